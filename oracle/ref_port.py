@@ -1,0 +1,112 @@
+"""Torch-CPU port of the reference's *procedure* for the hot path.  TEST INFRASTRUCTURE ONLY.
+
+``/root/reference`` does not travel to the GPU box, and the reference is pure
+Python (nothing to compile into ``oracle/_ref``), so this port is what
+``bench.py --impl reference`` and ``bench.py``'s ``cpu_baseline`` leg time on the
+box's host cores (``cpu_baseline.kind == "port"``).  It keeps the reference's
+execution structure -- one Python iteration per caption, each scoring that
+caption against every image with batched fp32 torch ops, including the
+reference's inline sanity checks (which are part of what the reference pays
+for) -- so its timing is representative of the reference's own CPU path:
+
+  words_loss loop            /root/reference/DMGAN+CLIP/code/miscc/losses.py:228-251
+  per-caption scoring        .../miscc/losses.py:95-216
+  class mask + two CEs       .../miscc/losses.py:224-232, 254-269
+  sent_loss                  .../miscc/losses.py:51-91
+
+``tests/test_oracle_vs_reference.py`` checks it against the live reference
+(loss and autograd gradients) whenever ``/root/reference`` is present, and
+``tests/test_oracle_golden.py`` against the recorded golden vectors everywhere.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def _unit(x, dim):
+    # losses.py:13-18: eps is ADDED to the norm
+    return x / (x.pow(2).sum(dim=dim, keepdim=True).sqrt() + 1e-8)
+
+
+def _same_class_mask(class_ids, n):
+    # losses.py:55-66 / :224-232 -- host loop, one numpy compare per sample
+    rows = []
+    for i in range(n):
+        row = (class_ids == class_ids[i]).astype(np.uint8)
+        row[i] = 0
+        rows.append(row[None, :])
+    return torch.from_numpy(np.concatenate(rows, 0).astype(bool))
+
+
+def score_caption(word_bdt, region_bdr, word_mask_bt1, gamma1, gamma2, checks=True):
+    """One caption (already tiled to the batch) against every image; losses.py:95-216."""
+    ctx = _unit(region_bdr.transpose(1, 2).contiguous(), 2)          # (B, R, D)
+    qry = _unit(word_bdt.transpose(1, 2).contiguous(), 2)            # (B, T, D)
+    s = torch.bmm(qry, ctx.transpose(1, 2))                          # (B, T, R)
+    s = s.masked_fill_(word_mask_bt1 == 0, float("-inf"))
+    if checks:                                                        # :133-137
+        for mk, row in zip(word_mask_bt1[0], s[0]):
+            if mk == 0:
+                assert row[0] == float("-inf")
+    p = F.softmax(s.transpose(1, 2), dim=-1)                         # (B, R, T): over words
+    if checks:                                                        # :145, :155-159
+        assert torch.isclose(p[0][0].sum(), torch.tensor(1.0), rtol=1e-5)
+        for mk, val in zip(word_mask_bt1[0], p[0][0]):
+            if mk == 0:
+                assert val == 0.0
+    a = F.softmax(gamma1 * p, dim=1)                                 # over regions
+    if checks:
+        assert torch.isnan(a).sum() == 0
+    a = a.permute(0, 2, 1)                                           # (B, T, R)
+    c = torch.bmm(a, ctx)                                            # (B, T, D)
+    if checks:
+        assert torch.isnan(c).sum() == 0
+    rho = F.cosine_similarity(c, qry, dim=2, eps=1e-6)               # (B, T)
+    e = (rho * gamma2).exp_().sum(dim=1)
+    return p, torch.log(torch.pow(e, 1.0 / gamma2))
+
+
+def words_loss(region_bdr, words_bdt, labels, class_ids, words_mask, gamma1, gamma2, gamma3, checks=True):
+    """losses.py:219-272.  Inputs in the reference layout (B,D,R) / (B,D,T)."""
+    n = words_bdt.shape[0]
+    sims = []
+    for i in range(n):
+        w = words_bdt[i].unsqueeze(0).contiguous().repeat(n, 1, 1)
+        m = words_mask[i].contiguous().repeat(n, 1).unsqueeze(-1)
+        _, r_qd = score_caption(w, region_bdr, m, gamma1, gamma2, checks)
+        sims.append(r_qd)
+    sim = torch.stack(sims) * gamma3
+    if class_ids is not None:
+        sim.data.masked_fill_(_same_class_mask(class_ids, n), float("-inf"))
+    return F.cross_entropy(sim, labels), F.cross_entropy(sim.transpose(0, 1), labels)
+
+
+def sent_loss(img_bd, txt_bd, labels, class_ids, gamma3, eps=1e-8):
+    """losses.py:51-91."""
+    n = img_bd.shape[0]
+    a, b = img_bd.unsqueeze(0), txt_bd.unsqueeze(0)
+    na = torch.norm(a, 2, dim=2, keepdim=True)
+    nb = torch.norm(b, 2, dim=2, keepdim=True)
+    sc = torch.bmm(a, b.transpose(1, 2)) / torch.bmm(na, nb.transpose(1, 2)).clamp(min=eps) * gamma3
+    sc = sc.squeeze(0)
+    if class_ids is not None:
+        sc.data.masked_fill_(_same_class_mask(class_ids, n), float("-inf"))
+    return F.cross_entropy(sc, labels), F.cross_entropy(sc.transpose(0, 1), labels)
+
+
+def step(x, gammas=(4.0, 5.0, 10.0), checks=True):
+    """One words_loss + sent_loss forward + backward on a ``make_inputs`` dict (numpy).
+    Returns dict(losses..., grads...) as numpy."""
+    w = torch.tensor(x["words"], dtype=torch.float32, requires_grad=True)
+    r = torch.tensor(x["regions"], dtype=torch.float32, requires_grad=True)
+    si = torch.tensor(x["img"], dtype=torch.float32, requires_grad=True)
+    st = torch.tensor(x["sent"], dtype=torch.float32, requires_grad=True)
+    lab = torch.tensor(x["labels"], dtype=torch.int64)
+    m = torch.tensor(x["mask"], dtype=torch.int64)
+    w0, w1 = words_loss(r.permute(0, 2, 1), w.permute(0, 2, 1), lab, x["class_ids"], m, *gammas, checks=checks)
+    s0, s1 = sent_loss(si, st, lab, x["class_ids"], gammas[2])
+    (w0 + w1 + s0 + s1).backward()
+    return dict(w_loss0=w0.item(), w_loss1=w1.item(), s_loss0=s0.item(), s_loss1=s1.item(),
+                dwords=w.grad.numpy(), dregions=r.grad.numpy(), dimg=si.grad.numpy(), dtxt=st.grad.numpy())

@@ -1,0 +1,147 @@
+"""Import the UNMODIFIED reference (``/root/reference``) in the build container.  TEST INFRASTRUCTURE ONLY.
+
+Used by ``oracle/make_golden.py`` (to record golden vectors) and by
+``tests/test_oracle_vs_reference.py`` (live comparison, skipped where
+``/root/reference`` does not exist, e.g. on the GPU box).  Nothing under
+``/root/reference`` is modified or copied; this file only arranges for
+``miscc/losses.py`` and ``GlobalAttention.py`` to import:
+
+  * ``easydict`` is not installed -> an in-memory stand-in module
+    (needed by miscc/config.py:6);
+  * on a CPU-only host losses.py:127 calls ``.cuda()`` and losses.py:145 calls
+    ``.get_device()``; both are neutralised on the Tensor class *only while a
+    reference function runs* (context manager), and ``cfg.CUDA`` is set False.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+import sys
+import types
+import warnings
+
+REF_ROOT = "/root/reference/DMGAN+CLIP/code"
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "miscc", "losses.py"))
+
+
+class _EasyDict(dict):
+    def __init__(self, d=None, **kw):
+        super().__init__()
+        for k, v in dict(d or {}, **kw).items():
+            setattr(self, k, v)
+
+    def __setattr__(self, k, v):
+        if isinstance(v, dict) and not isinstance(v, _EasyDict):
+            v = _EasyDict(v)
+        super().__setattr__(k, v)
+        super().__setitem__(k, v)
+
+    __setitem__ = __setattr__
+
+
+_mods = None
+
+
+def load():
+    """Returns (losses_module, GlobalAttention_module, cfg)."""
+    global _mods
+    if _mods is not None:
+        return _mods
+    if not available():
+        raise RuntimeError("reference sources not present at " + REF_ROOT)
+    if "easydict" not in sys.modules:
+        m = types.ModuleType("easydict")
+        m.EasyDict = _EasyDict
+        sys.modules["easydict"] = m
+    # the reference's package is called ``miscc`` -- make sure ours is not shadowing it
+    for name in [k for k in sys.modules if k == "miscc" or k.startswith("miscc.") or k == "GlobalAttention"]:
+        del sys.modules[name]
+    sys.path.insert(0, REF_ROOT)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            import GlobalAttention as ga          # noqa: E402
+            from miscc import losses              # noqa: E402
+            from miscc.config import cfg          # noqa: E402
+    finally:
+        sys.path.remove(REF_ROOT)
+    # keep them out of sys.modules so the product's own ``miscc`` drop-in can be imported later
+    for name in [k for k in sys.modules if k == "miscc" or k.startswith("miscc.") or k == "GlobalAttention"]:
+        del sys.modules[name]
+    _mods = (losses, ga, cfg)
+    return _mods
+
+
+@contextlib.contextmanager
+def cpu_patches():
+    """Neutralise the two hard-coded CUDA-isms (losses.py:127, :145) on a CPU-only host."""
+    import torch
+    losses, ga, cfg = load()
+    if torch.cuda.is_available():
+        cfg.CUDA = True
+        yield
+        return
+    old_cuda, old_getdev, old_flag = torch.Tensor.cuda, torch.Tensor.get_device, cfg.CUDA
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.Tensor.get_device = lambda self: self.device
+    cfg.CUDA = False
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda, torch.Tensor.get_device, cfg.CUDA = old_cuda, old_getdev, old_flag
+
+
+def ref_words_loss(words_btd, regions_brd, mask, labels, class_ids, gammas, cap_lens=None):
+    """Run the reference words_loss (losses.py:219) on (B,T,D)/(B,R,D) numpy inputs, fp32.
+    Returns dict(loss0, loss1, dwords, dregions) with gradients of loss0+loss1."""
+    import numpy as np
+    import torch
+    losses, _, _ = load()
+    w = torch.tensor(np.asarray(words_btd), dtype=torch.float32, requires_grad=True)
+    r = torch.tensor(np.asarray(regions_brd), dtype=torch.float32, requires_grad=True)
+    B = w.shape[0]
+    m = torch.tensor(np.asarray(mask), dtype=torch.int64)
+    lab = torch.tensor(np.asarray(labels), dtype=torch.int64)
+    cl = torch.tensor(np.asarray(cap_lens if cap_lens is not None else np.asarray(mask).sum(1)), dtype=torch.int64)
+    with cpu_patches():
+        l0, l1, attn = losses.words_loss(r.permute(0, 2, 1), w.permute(0, 2, 1), lab, cl,
+                                         None if class_ids is None else np.asarray(class_ids), B, m,
+                                         float(gammas[0]), float(gammas[1]), float(gammas[2]))
+        (l0 + l1).backward()
+    return dict(loss0=float(l0.detach()), loss1=float(l1.detach()), dwords=w.grad.numpy().copy(), dregions=r.grad.numpy().copy(),
+                attn0=attn[0].detach().numpy().copy())
+
+
+def ref_sent_loss(img, txt, labels, class_ids, gamma3):
+    import numpy as np
+    import torch
+    losses, _, cfg = load()
+    a = torch.tensor(np.asarray(img), dtype=torch.float32, requires_grad=True)
+    b = torch.tensor(np.asarray(txt), dtype=torch.float32, requires_grad=True)
+    lab = torch.tensor(np.asarray(labels), dtype=torch.int64)
+    cfg.TRAIN.SMOOTH.GAMMA3 = float(gamma3)
+    with cpu_patches():
+        l0, l1 = losses.sent_loss(a, b, lab, None if class_ids is None else np.asarray(class_ids), a.shape[0])
+        (l0 + l1).backward()
+    return dict(loss0=float(l0.detach()), loss1=float(l1.detach()), dimg=a.grad.numpy().copy(), dtxt=b.grad.numpy().copy())
+
+
+def ref_func_attention(query_btd, context_brd, gamma1, query_mask, d_wc=None):
+    import numpy as np
+    import torch
+    _, ga, _ = load()
+    q = torch.tensor(np.asarray(query_btd), dtype=torch.float32, requires_grad=True)
+    c = torch.tensor(np.asarray(context_brd), dtype=torch.float32, requires_grad=True)
+    m = torch.tensor(np.asarray(query_mask), dtype=torch.int64).unsqueeze(1)
+    with cpu_patches(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        wc, attn = ga.func_attention(q.permute(0, 2, 1), c.permute(0, 2, 1), float(gamma1), m)
+        out = dict(wc=wc.detach().numpy().copy(), attn=attn.detach().numpy().copy())
+        if d_wc is not None:
+            wc.backward(torch.tensor(np.asarray(d_wc), dtype=torch.float32))
+            out["dquery"] = q.grad.numpy().copy()
+            out["dcontext"] = c.grad.numpy().copy()
+    return out
