@@ -1,0 +1,19 @@
+# Builds libdamsm_b200.so (hand-written sm_100a CUDA behind a C ABI) in-tree.
+NVCC ?= /usr/local/cuda/bin/nvcc
+PKG := t2i_clip-gan_b200
+SRC := $(wildcard $(PKG)/csrc/*.cu)
+HDR := $(wildcard $(PKG)/csrc/*.cuh) include/damsm_b200.h
+OUT := $(PKG)/libdamsm_b200.so
+NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC \
+           -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr
+
+all: $(OUT)
+
+$(OUT): $(SRC) $(HDR)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRC) -lcuda
+
+ptxas-info:
+	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o /tmp/damsm_ptxas.so $(SRC) -lcuda 2>&1 | grep -E "Compiling|registers|spill" 
+
+clean:
+	rm -f $(OUT)

@@ -1,0 +1,141 @@
+/*
+ * damsm_b200.h -- C ABI of libdamsm_b200.so: the DAMSM word/sentence matching loss of
+ * dgjun32/T2I_CLIP-GAN as hand-written sm_100a CUDA kernels.
+ *
+ * The reference has no FFI of its own: the hot path sits behind plain Python functions
+ *   words_loss / similarity_text_image   DMGAN+CLIP/code/miscc/losses.py:219-272, 95-216
+ *   sent_loss                            DMGAN+CLIP/code/miscc/losses.py:51-91
+ *   l2norm                               DMGAN+CLIP/code/miscc/losses.py:13-18
+ *   class_ids masking + 2x CrossEntropy  DMGAN+CLIP/code/miscc/losses.py:55-66,84-88,224-232,254-269
+ *   func_attention                       DMGAN+CLIP/code/GlobalAttention.py:38-160
+ * so the entry points below are what a ctypes stub inside those functions binds
+ * (INTEGRATION.md shows the stub).  Each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream,
+ *     allocates nothing, never synchronises and is CUDA-graph capturable;
+ *   - every function returns 0 on success; otherwise damsm_last_error() (host, thread-local)
+ *     describes the failure.  There is no CPU fallback anywhere.
+ *   - index names: caption (row) i in [0,br), image (column) j in [0,bc), word t in [0,T),
+ *     region r in [0,R), feature d in [0,D).  A rank that owns a row shard of the global batch
+ *     passes row_offset = global index of its first caption and b_total = global batch.
+ *   - "hat" tensors are l2-normalised, contiguous, D innermost: qhat (br,T,D), vhat (bc,R,D).
+ */
+#ifndef DAMSM_B200_H_
+#define DAMSM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DAMSM_API __attribute__((visibility("default")))
+#else
+#define DAMSM_API
+#endif
+
+#define DAMSM_ABI_VERSION 1
+
+#define DAMSM_F32 0
+#define DAMSM_BF16 1
+#define DAMSM_F16 2
+
+/* limits of the fused per-pair kernels */
+#define DAMSM_MAX_T 128
+#define DAMSM_MAX_R 256
+
+DAMSM_API int damsm_version(void);
+DAMSM_API const char *damsm_last_error(void);
+/* host: properties of the current device (all out pointers are host pointers) */
+DAMSM_API int damsm_device_info(int *sm_count, int *cc_major, int *cc_minor, int *max_smem_optin);
+
+/* ---- l2norm prologue / epilogue (losses.py:13-18, applied at :115-116; GlobalAttention.py:60-61) --------
+ * x is viewed as (nb, nv, D) through element strides (sb, sv, sd), so the reference's permuted
+ * (B,D,T)/(B,D,R) views, the CLS-sliced region view and 4-D (B,D,h,w) tensors are read in place.
+ * xhat = x / (||x||_2 + 1e-8).  Outputs (each may be NULL): xhat_f32 (nb,nv,D), xhat_bf16 (nb,nv,D),
+ * norm (nb,nv) = ||x||, unorm (nb,nv) = ||xhat|| (the norm CosineSimilarity sees at losses.py:197). */
+DAMSM_API int damsm_l2norm_fwd(const void *x, int dtype, int64_t nb, int64_t nv, int64_t d,
+                     int64_t sb, int64_t sv, int64_t sd,
+                     float *xhat_f32, void *xhat_bf16, float *norm, float *unorm, void *stream);
+/* dx = (dxhat' - (xhat.dxhat') x/||x||) / (||x||+1e-8) with dxhat' = dxhat - kq*xhat/unorm^2
+ * (kq may be NULL; it carries the cosine's dependence on ||qhat||).  dx has x's dtype and is written
+ * through element strides (dsb, dsv, dsd). */
+DAMSM_API int damsm_l2norm_bwd(const void *x, int dtype, int64_t nb, int64_t nv, int64_t d,
+                     int64_t sb, int64_t sv, int64_t sd,
+                     const float *norm, const float *dxhat, const float *kq,
+                     void *dx, int64_t dsb, int64_t dsv, int64_t dsd, void *stream);
+
+/* ---- per-image Gram matrices G_j = vhat_j vhat_j^T (bc,R,R): ||c_t||^2 = a_t^T G a_t replaces the
+ * second D-wide bmm of losses.py:182 by an R-wide one --------------------------------------------------- */
+DAMSM_API int damsm_gram_f32(const float *vhat, int64_t bc, int64_t r, int64_t d, float *gram, void *stream);
+/* dvhat_j -= H_j vhat_j  (H_j = sum_i A^T diag(b) A accumulated by damsm_words_bwd_f32) */
+DAMSM_API int damsm_gram_bwd_f32(const float *hmat, const float *vhat, int64_t bc, int64_t r, int64_t d,
+                       float *dvhat, void *stream);
+
+/* ---- word-region matching scores, exact fp32 path (losses.py:95-216 for every (i,j), :228-254) ------
+ * sim[i*bc + j] = gamma3 * (1/gamma2) log sum_t exp(gamma2 * cos(c_ijt, qhat_it))   (not yet class-masked)
+ * mask (br,T): 1 = word, 0 = padding (masked only in the softmax over words, losses.py:127). */
+DAMSM_API int damsm_words_fwd_f32(const float *qhat, const float *vhat, const float *gram, const float *unorm,
+                        const uint8_t *mask, int64_t br, int64_t bc, int64_t t, int64_t r, int64_t d,
+                        float gamma1, float gamma2, float gamma3, float *sim, void *stream);
+/* Backward of the above fused with the backward of both cross-entropies: the gradient of
+ * gscale[0]*loss0 + gscale[1]*loss1 w.r.t. sim is rebuilt per pair from sim/row_lse/col_lse/labels,
+ * S, P, A are recomputed on chip.  Outputs are ACCUMULATED (caller zeroes them):
+ *   dqhat (br,T,D), dvhat (bc,R,D), hmat (bc,R,R), kq (br,T).  gscale: device float[2]. */
+DAMSM_API int damsm_words_bwd_f32(const float *qhat, const float *vhat, const float *gram, const float *unorm,
+                        const uint8_t *mask, const float *sim, const float *row_lse, const float *col_lse,
+                        const int64_t *labels, const float *gscale, int64_t row_offset, int64_t b_total,
+                        int64_t br, int64_t bc, int64_t t, int64_t r, int64_t d,
+                        float gamma1, float gamma2, float gamma3,
+                        float *dqhat, float *dvhat, float *hmat, float *kq, void *stream);
+/* host: dynamic shared memory the fused fp32 pair kernel needs for (T,R); <0 if unsupported */
+DAMSM_API int64_t damsm_words_f32_smem_bytes(int64_t t, int64_t r);
+
+/* ---- class_ids masking + both CrossEntropyLoss() (losses.py:55-66,84-88 / :224-232,256-269) -----------
+ * logits (br,bc) row block of the (b_total x b_total) matrix.  In place: logits[i][j] = -inf where
+ * cls_rows[i]==cls_cols[j] and j != row_offset+i (cls_* may be NULL = no masking).
+ * row_lse (br) is complete; col_max/col_sum (bc) are this block's partial max / sum exp(x-max). */
+DAMSM_API int damsm_ce_stats_f32(float *logits, const int64_t *cls_rows, const int64_t *cls_cols, int64_t row_offset,
+                       int64_t br, int64_t bc, float *row_lse, float *col_max, float *col_sum, void *stream);
+/* out[0] = (1/b_total) sum_i (row_lse[i] - logits[i][labels[row_offset+i]])           (CE over columns)
+ * out[1] = (1/b_total) sum_{j: labels[j] is a local row} (col_lse[j] - logits[labels[j]-row_offset][j])
+ * labels: (b_total) global int64; col_lse (bc) is the COMPLETE column log-sum-exp. */
+DAMSM_API int damsm_ce_losses_f32(const float *logits, const float *row_lse, const float *col_lse,
+                        const int64_t *labels, int64_t row_offset, int64_t br, int64_t bc, int64_t b_total,
+                        float *out2, void *stream);
+
+/* ---- sentence-level logits (losses.py:74-79): logits[i][j] = gamma3 * a_i.b_j / max(|a_i||b_j|, eps) ---- */
+DAMSM_API int damsm_cos_logits_f32(const float *a, int64_t lda, const float *b, int64_t ldb,
+                         int64_t br, int64_t bc, int64_t d, float gamma3, float eps,
+                         float *logits, float *na, float *nb, void *stream);
+/* backward incl. both CEs; work: scratch of br*bc + br + bc floats; da (br,d), db (bc,d) are OVERWRITTEN */
+DAMSM_API int damsm_cos_logits_bwd_f32(const float *a, int64_t lda, const float *b, int64_t ldb,
+                             const float *na, const float *nb, const float *logits,
+                             const float *row_lse, const float *col_lse, const int64_t *labels,
+                             const float *gscale, int64_t row_offset, int64_t b_total,
+                             int64_t br, int64_t bc, int64_t d, float gamma3, float eps,
+                             float *work, float *da, float *db, void *stream);
+
+/* ---- func_attention (GlobalAttention.py:38-160): one (caption b, image b) pair per batch element -------
+ * wc (B,T,D) = A . context_RAW (line :153), attn (B,T,R) = softmax over words (line :104),
+ * attn2 (B,T,R) = softmax over regions of gamma1*attn (saved for backward).
+ * ctx is the raw context viewed as (B,R,D) through element strides. */
+DAMSM_API int damsm_func_attention_fwd_f32(const float *qhat, const float *vhat, const float *ctx,
+                                 int64_t csb, int64_t csr, int64_t csd, const uint8_t *mask,
+                                 int64_t b, int64_t t, int64_t r, int64_t d, float gamma1,
+                                 float *wc, float *attn, float *attn2, void *stream);
+/* d_wc (B,T,D) and d_attn (B,T,R) may each be NULL.  Outputs OVERWRITTEN: dqhat (B,T,D),
+ * dvhat (B,R,D), dctx (B,R,D) (gradient through the raw-context product only). */
+DAMSM_API int damsm_func_attention_bwd_f32(const float *qhat, const float *vhat, const float *ctx,
+                                 int64_t csb, int64_t csr, int64_t csd,
+                                 const float *attn, const float *attn2, const float *d_wc, const float *d_attn,
+                                 int64_t b, int64_t t, int64_t r, int64_t d, float gamma1,
+                                 float *dqhat, float *dvhat, float *dctx, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAMSM_B200_H_ */

@@ -1,0 +1,90 @@
+"""ctypes binding of libdamsm_b200.so (the C ABI declared in include/damsm_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, an exception is
+raised.  PyTorch is used by the callers only to own device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libdamsm_b200.so")
+
+_p, _i, _l, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> argument ctypes, in header order (return type is int unless listed in _RESTYPE)
+SIGNATURES = {
+    "damsm_version": [],
+    "damsm_last_error": [],
+    "damsm_device_info": [_p, _p, _p, _p],
+    "damsm_l2norm_fwd": [_p, _i, _l, _l, _l, _l, _l, _l, _p, _p, _p, _p, _p],
+    "damsm_l2norm_bwd": [_p, _i, _l, _l, _l, _l, _l, _l, _p, _p, _p, _p, _l, _l, _l, _p],
+    "damsm_gram_f32": [_p, _l, _l, _l, _p, _p],
+    "damsm_gram_bwd_f32": [_p, _p, _l, _l, _l, _p, _p],
+    "damsm_words_fwd_f32": [_p, _p, _p, _p, _p, _l, _l, _l, _l, _l, _f, _f, _f, _p, _p],
+    "damsm_words_bwd_f32": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _l, _l, _l, _f, _f, _f,
+                            _p, _p, _p, _p, _p],
+    "damsm_words_f32_smem_bytes": [_l, _l],
+    "damsm_ce_stats_f32": [_p, _p, _p, _l, _l, _l, _p, _p, _p, _p],
+    "damsm_ce_losses_f32": [_p, _p, _p, _p, _l, _l, _l, _l, _p, _p],
+    "damsm_cos_logits_f32": [_p, _l, _p, _l, _l, _l, _l, _f, _f, _p, _p, _p, _p],
+    "damsm_cos_logits_bwd_f32": [_p, _l, _p, _l, _p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _l, _f, _f,
+                                 _p, _p, _p, _p],
+    "damsm_func_attention_fwd_f32": [_p, _p, _p, _l, _l, _l, _p, _l, _l, _l, _l, _f, _p, _p, _p, _p],
+    "damsm_func_attention_bwd_f32": [_p, _p, _p, _l, _l, _l, _p, _p, _p, _p, _l, _l, _l, _l, _f, _p, _p, _p, _p],
+}
+_RESTYPE = {"damsm_last_error": C.c_char_p, "damsm_words_f32_smem_bytes": C.c_int64}
+
+_lib = None
+
+
+class DamsmError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA sources in-tree for sm_100a (``make`` at the repo root)."""
+    cmd = ["make", "-C", _ROOT, "all"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise DamsmError("building libdamsm_b200.so failed")
+    return LIB_PATH
+
+
+def load():
+    """Load (once) and type the library.  Raises DamsmError when the .so is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise DamsmError(
+            f"{LIB_PATH} not found: the DAMSM kernels are CUDA-only (no CPU fallback). "
+            "Build it with `make` at the repository root or `python -c 'import __graft_entry__ as g; g.build()'`.")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _RESTYPE.get(name, C.c_int)
+    if lib.damsm_version() != 1:
+        raise DamsmError("libdamsm_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point and raise on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise DamsmError(f"{name} failed ({rc}): {lib.damsm_last_error().decode(errors='replace')}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

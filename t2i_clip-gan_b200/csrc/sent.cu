@@ -1,0 +1,144 @@
+// Sentence-level matching logits and their backward (losses.py:74-88):
+//   logits[i][j] = gamma3 * a_i.b_j / max(|a_i| |b_j|, eps)       (eps clamps the PRODUCT of the norms)
+// rows = images (cnn_code), columns = captions (rnn_code); the masked bidirectional CE is shared with the
+// word loss (ce.cu).  O(B^2 D) work -- 3 orders of magnitude below the word loss -- so plain fp32 SIMT GEMMs.
+#include "common.cuh"
+#include "gemm_f32.cuh"
+
+namespace damsm {
+
+__global__ void __launch_bounds__(256) row_norm_kernel(const float *__restrict__ x, int64_t ld, int n, int d,
+                                                       float *__restrict__ out) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float s = 0.f;
+  for (int k = lane; k < d; k += 32) { const float v = x[(int64_t)row * ld + k]; s = fmaf(v, v, s); }
+  s = warp_sum(s);
+  if (lane == 0) out[row] = sqrtf(s);
+}
+
+__global__ void __launch_bounds__(256) cos_scale_kernel(float *__restrict__ logits, const float *__restrict__ na,
+                                                        const float *__restrict__ nb, int br, int bc, float gamma3,
+                                                        float eps) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)br * bc) return;
+  const int i = (int)(e / bc), j = (int)(e - (int64_t)i * bc);
+  logits[e] = logits[e] / fmaxf(na[i] * nb[j], eps) * gamma3;
+}
+
+// work[i][j] = g_ij / den_ij (coefficient of the dot product); rowc[i] += sum_j gn_ij nb_j ; colc[j] += sum_i gn_ij na_i
+// with gn = -g * dot / den^2 where the clamp is inactive (gradient of the norm product), g = dL/d(dot/den).
+__global__ void __launch_bounds__(256) cos_bwd_coef_kernel(const float *__restrict__ logits, const float *__restrict__ na,
+                                                           const float *__restrict__ nb, const float *__restrict__ row_lse,
+                                                           const float *__restrict__ col_lse,
+                                                           const int64_t *__restrict__ labels,
+                                                           const float *__restrict__ gscale, int64_t row_offset,
+                                                           int64_t b_total, int br, int bc, float gamma3, float eps,
+                                                           float *__restrict__ work, float *__restrict__ rowc,
+                                                           float *__restrict__ colc) {
+  const int i = blockIdx.x;
+  const int64_t gi = row_offset + i;
+  const int64_t li = labels ? labels[gi] : gi;
+  const float nai = na[i], rl = row_lse[i], g0 = gscale[0], g1 = gscale[1];
+  float racc = 0.f;
+  for (int j = threadIdx.x; j < bc; j += blockDim.x) {
+    const float s = logits[(int64_t)i * bc + j];
+    float w = 0.f;
+    if (s != -INFINITY) {
+      const int64_t lj = labels ? labels[j] : (int64_t)j;
+      const float gr = expf(s - rl) - (li == j ? 1.f : 0.f);
+      const float gc = expf(s - col_lse[j]) - (lj == gi ? 1.f : 0.f);
+      const float g = (g0 * gr + g1 * gc) / (float)b_total * gamma3;   // d/d(dot/den)
+      const float nn = nai * nb[j];
+      const float den = fmaxf(nn, eps);
+      w = g / den;
+      if (nn > eps) {
+        const float ratio = s / gamma3;               // dot / den
+        const float gn = -g * ratio / den;            // d/d(na*nb)
+        racc = fmaf(gn, nb[j], racc);
+        atomicAdd(colc + j, gn * nai);
+      }
+    }
+    work[(int64_t)i * bc + j] = w;
+  }
+  __shared__ float red[8];
+  racc = warp_sum(racc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = racc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    rowc[i] = s;
+  }
+}
+
+// x_grad[row][:] += coef[row] * x[row][:] / |x[row]|
+__global__ void __launch_bounds__(256) norm_term_kernel(float *__restrict__ gx, const float *__restrict__ x, int64_t ld,
+                                                        const float *__restrict__ coef, const float *__restrict__ nrm,
+                                                        int n, int d) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)n * d) return;
+  const int row = (int)(e / d), k = (int)(e - (int64_t)row * d);
+  const float nr = nrm[row];
+  if (nr > 0.f) gx[e] += coef[row] * x[(int64_t)row * ld + k] / nr;
+}
+
+}  // namespace damsm
+
+using namespace damsm;
+
+extern "C" int damsm_cos_logits_f32(const float *a, int64_t lda, const float *b, int64_t ldb, int64_t br, int64_t bc,
+                                    int64_t d, float gamma3, float eps, float *logits, float *na, float *nb,
+                                    void *stream) {
+  DAMSM_REQUIRE(a && b && logits && na && nb && d > 0, "cos_logits: bad arguments");
+  if (br == 0 || bc == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  row_norm_kernel<<<(unsigned)((br + 7) / 8), 256, 0, st>>>(a, lda, (int)br, (int)d, na);
+  row_norm_kernel<<<(unsigned)((bc + 7) / 8), 256, 0, st>>>(b, ldb, (int)bc, (int)d, nb);
+  GemmDesc g{};
+  g.a = a; g.a_m = lda; g.a_k = 1;
+  g.b = b; g.b_k = 1; g.b_n = ldb;
+  g.c = logits; g.c_m = bc; g.c_n = 1;
+  g.m = (int)br; g.n = (int)bc; g.k = (int)d; g.batch = 1; g.alpha = 1.f; g.beta = 0.f;
+  int rc = launch_gemm_f32(g, st);
+  if (rc) return rc;
+  const int64_t n = br * bc;
+  cos_scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(logits, na, nb, (int)br, (int)bc, gamma3, eps);
+  return check_launch("cos_logits");
+}
+
+extern "C" int damsm_cos_logits_bwd_f32(const float *a, int64_t lda, const float *b, int64_t ldb, const float *na,
+                                        const float *nb, const float *logits, const float *row_lse,
+                                        const float *col_lse, const int64_t *labels, const float *gscale,
+                                        int64_t row_offset, int64_t b_total, int64_t br, int64_t bc, int64_t d,
+                                        float gamma3, float eps, float *work, float *da, float *db, void *stream) {
+  DAMSM_REQUIRE(a && b && na && nb && logits && row_lse && col_lse && gscale && work && da && db,
+                "cos_logits_bwd: null pointer");
+  if (br == 0 || bc == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  // coefficient vectors live at the tail of `work`?  No: keep the ABI simple -- reuse da/db's first columns is
+  // unsafe, so the wrapper passes work of size br*bc + br + bc.
+  float *rowc = work + br * bc;
+  float *colc = rowc + br;
+  DAMSM_CUDA(cudaMemsetAsync(colc, 0, sizeof(float) * bc, st));
+  cos_bwd_coef_kernel<<<(unsigned)br, 256, 0, st>>>(logits, na, nb, row_lse, col_lse, labels, gscale, row_offset,
+                                                    b_total, (int)br, (int)bc, gamma3, eps, work, rowc, colc);
+  GemmDesc g{};
+  // da = work (br x bc) @ b (bc x d)
+  g.a = work; g.a_m = bc; g.a_k = 1;
+  g.b = b; g.b_k = ldb; g.b_n = 1;
+  g.c = da; g.c_m = d; g.c_n = 1;
+  g.m = (int)br; g.n = (int)d; g.k = (int)bc; g.batch = 1; g.alpha = 1.f; g.beta = 0.f;
+  int rc = launch_gemm_f32(g, st);
+  if (rc) return rc;
+  // db = work^T (bc x br) @ a (br x d)
+  g.a = work; g.a_m = 1; g.a_k = bc;
+  g.b = a; g.b_k = lda; g.b_n = 1;
+  g.c = db; g.c_m = d; g.c_n = 1;
+  g.m = (int)bc; g.n = (int)d; g.k = (int)br;
+  rc = launch_gemm_f32(g, st);
+  if (rc) return rc;
+  norm_term_kernel<<<(unsigned)((br * d + 255) / 256), 256, 0, st>>>(da, a, lda, rowc, na, (int)br, (int)d);
+  norm_term_kernel<<<(unsigned)((bc * d + 255) / 256), 256, 0, st>>>(db, b, ldb, colc, nb, (int)bc, (int)d);
+  return check_launch("cos_logits_bwd");
+}

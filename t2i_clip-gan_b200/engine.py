@@ -1,0 +1,200 @@
+"""Block-level compute engine: thin, typed wrappers over the C ABI (include/damsm_b200.h).
+
+``CudaEngine`` is the product engine -- every method launches hand-written sm_100a kernels from
+libdamsm_b200.so on the current CUDA stream and raises if that is not possible.  The host logic in
+``ops.py`` (autograd plumbing, sharding, collectives) only talks to this small interface, which is what
+lets the CPU-only ``gloo`` tests exercise the multi-rank logic with a checker engine injected from
+``tests/`` -- the package itself contains no CPU implementation.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.DamsmError(
+                "DAMSM kernels are CUDA-only (sm_100a); got a CPU tensor and there is no CPU fallback")
+
+
+class CudaEngine:
+    """Exact-fp32 SIMT path (precision='fp32') and bf16 tcgen05 path (precision='bf16')."""
+
+    name = "cuda"
+
+    def __init__(self, precision: str = "fp32"):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError(f"unknown precision {precision!r}")
+        self.precision = precision
+        _lib.load()
+
+    # ---- l2norm ---------------------------------------------------------------------------------------
+    def l2norm_fwd(self, x3: torch.Tensor, want_bf16: bool = False):
+        """x3: (nb, nv, D) strided view.  Returns (xhat_f32, xhat_bf16|None, norm, unorm)."""
+        _require_cuda(x3)
+        if x3.dtype not in _DTYPE_CODE:
+            raise TypeError(f"unsupported dtype {x3.dtype}")
+        nb, nv, d = x3.shape
+        dev = x3.device
+        xhat = torch.empty((nb, nv, d), device=dev, dtype=torch.float32)
+        xhat16 = torch.empty((nb, nv, d), device=dev, dtype=torch.bfloat16) if want_bf16 else None
+        norm = torch.empty((nb, nv), device=dev, dtype=torch.float32)
+        unorm = torch.empty((nb, nv), device=dev, dtype=torch.float32)
+        sb, sv, sd = x3.stride()
+        _lib.call("damsm_l2norm_fwd", x3.data_ptr(), _DTYPE_CODE[x3.dtype], nb, nv, d, sb, sv, sd,
+                  xhat.data_ptr(), _lib.ptr(xhat16), norm.data_ptr(), unorm.data_ptr(), _stream())
+        return xhat, xhat16, norm, unorm
+
+    def l2norm_bwd(self, x3: torch.Tensor, norm, dxhat, kq=None):
+        """Gradient w.r.t. the raw x3, returned as a tensor with x3's shape and dtype whose memory
+        layout matches x3's (so autograd can hand it straight back through the permute)."""
+        _require_cuda(x3, norm, dxhat, kq)
+        nb, nv, d = x3.shape
+        dx = torch.empty_strided(x3.shape, _dense_strides_like(x3), device=x3.device, dtype=x3.dtype)
+        sb, sv, sd = x3.stride()
+        dsb, dsv, dsd = dx.stride()
+        dxhat = dxhat.contiguous()
+        _lib.call("damsm_l2norm_bwd", x3.data_ptr(), _DTYPE_CODE[x3.dtype], nb, nv, d, sb, sv, sd,
+                  norm.data_ptr(), dxhat.data_ptr(), _lib.ptr(kq), dx.data_ptr(), dsb, dsv, dsd, _stream())
+        return dx
+
+    # ---- word / region scores ---------------------------------------------------------------------------
+    def words_prepare_columns(self, vhat: torch.Tensor):
+        """Per-image side data derived from vhat (bc,R,D): the Gram matrices."""
+        bc, r, d = vhat.shape
+        gram = torch.empty((bc, r, r), device=vhat.device, dtype=torch.float32)
+        _lib.call("damsm_gram_f32", vhat.data_ptr(), bc, r, d, gram.data_ptr(), _stream())
+        return gram
+
+    def words_fwd(self, qhat, vhat, gram, unorm, mask_u8, gammas):
+        _require_cuda(qhat, vhat, gram, unorm, mask_u8)
+        br, t, d = qhat.shape
+        bc, r, _ = vhat.shape
+        sim = torch.empty((br, bc), device=qhat.device, dtype=torch.float32)
+        _lib.call("damsm_words_fwd_f32", qhat.data_ptr(), vhat.data_ptr(), gram.data_ptr(), unorm.data_ptr(),
+                  mask_u8.data_ptr(), br, bc, t, r, d, float(gammas[0]), float(gammas[1]), float(gammas[2]),
+                  sim.data_ptr(), _stream())
+        return sim
+
+    def words_bwd(self, qhat, vhat, gram, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
+                  row_offset, b_total, gammas):
+        """Returns (dqhat (br,T,D), dvhat (bc,R,D) partial over this rank's rows, kq (br,T))."""
+        br, t, d = qhat.shape
+        bc, r, _ = vhat.shape
+        dev = qhat.device
+        dqhat = torch.zeros((br, t, d), device=dev, dtype=torch.float32)
+        dvhat = torch.zeros((bc, r, d), device=dev, dtype=torch.float32)
+        hmat = torch.zeros((bc, r, r), device=dev, dtype=torch.float32)
+        kq = torch.zeros((br, t), device=dev, dtype=torch.float32)
+        _lib.call("damsm_words_bwd_f32", qhat.data_ptr(), vhat.data_ptr(), gram.data_ptr(), unorm.data_ptr(),
+                  mask_u8.data_ptr(), sim.data_ptr(), row_lse.data_ptr(), col_lse.data_ptr(), _lib.ptr(labels),
+                  gscale.data_ptr(), int(row_offset), int(b_total), br, bc, t, r, d,
+                  float(gammas[0]), float(gammas[1]), float(gammas[2]),
+                  dqhat.data_ptr(), dvhat.data_ptr(), hmat.data_ptr(), kq.data_ptr(), _stream())
+        _lib.call("damsm_gram_bwd_f32", hmat.data_ptr(), vhat.data_ptr(), bc, r, d, dvhat.data_ptr(), _stream())
+        return dqhat, dvhat, kq
+
+    # ---- masked bidirectional cross-entropy ---------------------------------------------------------------
+    def ce_stats(self, logits, cls_rows, cls_cols, row_offset):
+        """Masks ``logits`` in place; returns (row_lse, col_max, col_sum)."""
+        _require_cuda(logits, cls_rows, cls_cols)
+        br, bc = logits.shape
+        dev = logits.device
+        row_lse = torch.empty(br, device=dev, dtype=torch.float32)
+        col_max = torch.empty(bc, device=dev, dtype=torch.float32)
+        col_sum = torch.empty(bc, device=dev, dtype=torch.float32)
+        _lib.call("damsm_ce_stats_f32", logits.data_ptr(), _lib.ptr(cls_rows), _lib.ptr(cls_cols), int(row_offset),
+                  br, bc, row_lse.data_ptr(), col_max.data_ptr(), col_sum.data_ptr(), _stream())
+        return row_lse, col_max, col_sum
+
+    def ce_losses(self, logits, row_lse, col_lse, labels, row_offset, b_total):
+        br, bc = logits.shape
+        out = torch.empty(2, device=logits.device, dtype=torch.float32)
+        _lib.call("damsm_ce_losses_f32", logits.data_ptr(), row_lse.data_ptr(), col_lse.data_ptr(),
+                  _lib.ptr(labels), int(row_offset), br, bc, int(b_total), out.data_ptr(), _stream())
+        return out
+
+    # ---- sentence logits ------------------------------------------------------------------------------------
+    def cos_logits(self, a, b, gamma3, eps):
+        _require_cuda(a, b)
+        br, d = a.shape
+        bc = b.shape[0]
+        dev = a.device
+        logits = torch.empty((br, bc), device=dev, dtype=torch.float32)
+        na = torch.empty(br, device=dev, dtype=torch.float32)
+        nb = torch.empty(bc, device=dev, dtype=torch.float32)
+        _lib.call("damsm_cos_logits_f32", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), br, bc, d,
+                  float(gamma3), float(eps), logits.data_ptr(), na.data_ptr(), nb.data_ptr(), _stream())
+        return logits, na, nb
+
+    def cos_logits_bwd(self, a, b, na, nb, logits, row_lse, col_lse, labels, gscale, row_offset, b_total,
+                       gamma3, eps):
+        br, d = a.shape
+        bc = b.shape[0]
+        dev = a.device
+        work = torch.empty(br * bc + br + bc, device=dev, dtype=torch.float32)
+        da = torch.empty((br, d), device=dev, dtype=torch.float32)
+        db = torch.empty((bc, d), device=dev, dtype=torch.float32)
+        _lib.call("damsm_cos_logits_bwd_f32", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
+                  na.data_ptr(), nb.data_ptr(), logits.data_ptr(), row_lse.data_ptr(), col_lse.data_ptr(),
+                  _lib.ptr(labels), gscale.data_ptr(), int(row_offset), int(b_total), br, bc, d,
+                  float(gamma3), float(eps), work.data_ptr(), da.data_ptr(), db.data_ptr(), _stream())
+        return da, db
+
+    # ---- func_attention -----------------------------------------------------------------------------------------
+    def func_attention_fwd(self, qhat, vhat, ctx3, mask_u8, gamma1):
+        _require_cuda(qhat, vhat, ctx3, mask_u8)
+        b, t, d = qhat.shape
+        r = vhat.shape[1]
+        dev = qhat.device
+        wc = torch.empty((b, t, d), device=dev, dtype=torch.float32)
+        attn = torch.empty((b, t, r), device=dev, dtype=torch.float32)
+        attn2 = torch.empty((b, t, r), device=dev, dtype=torch.float32)
+        csb, csr, csd = ctx3.stride()
+        _lib.call("damsm_func_attention_fwd_f32", qhat.data_ptr(), vhat.data_ptr(), ctx3.data_ptr(), csb, csr, csd,
+                  mask_u8.data_ptr(), b, t, r, d, float(gamma1), wc.data_ptr(), attn.data_ptr(), attn2.data_ptr(),
+                  _stream())
+        return wc, attn, attn2
+
+    def func_attention_bwd(self, qhat, vhat, ctx3, attn, attn2, d_wc, d_attn, gamma1):
+        b, t, d = qhat.shape
+        r = vhat.shape[1]
+        dev = qhat.device
+        dqhat = torch.empty((b, t, d), device=dev, dtype=torch.float32)
+        dvhat = torch.empty((b, r, d), device=dev, dtype=torch.float32)
+        dctx = torch.empty((b, r, d), device=dev, dtype=torch.float32)
+        csb, csr, csd = ctx3.stride()
+        _lib.call("damsm_func_attention_bwd_f32", qhat.data_ptr(), vhat.data_ptr(), ctx3.data_ptr(), csb, csr, csd,
+                  attn.data_ptr(), attn2.data_ptr(), _lib.ptr(d_wc), _lib.ptr(d_attn), b, t, r, d, float(gamma1),
+                  dqhat.data_ptr(), dvhat.data_ptr(), dctx.data_ptr(), _stream())
+        return dqhat, dvhat, dctx
+
+
+def _dense_strides_like(x: torch.Tensor):
+    """Strides of a dense tensor whose dimension order (by stride) matches ``x`` -- the layout autograd
+    would pick for a gradient flowing back through the same permute/slice."""
+    order = sorted(range(x.dim()), key=lambda i: (x.stride(i), -i), reverse=True)
+    strides = [0] * x.dim()
+    acc = 1
+    for i in reversed(order):
+        strides[i] = acc
+        acc *= x.shape[i]
+    return tuple(strides)
+
+
+_default_engines = {}
+
+
+def get_engine(precision: str = "fp32"):
+    if precision not in _default_engines:
+        _default_engines[precision] = CudaEngine(precision)
+    return _default_engines[precision]

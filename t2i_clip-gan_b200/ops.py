@@ -1,0 +1,328 @@
+"""Host logic of the DAMSM drop-ins: autograd plumbing, sharding by caption rows and the collectives.
+
+All arithmetic is done by the engine (``engine.CudaEngine`` -> libdamsm_b200.so).  What lives here is
+the reference's *interface* behaviour (DMGAN+CLIP/code/miscc/losses.py:51-91, 219-272;
+GlobalAttention.py:38-160) and the multi-GPU exchange steps of SURVEY.md 8(e):
+
+  forward   all_gather(vhat / sentence codes / class ids)  ->  local (B/N x B) block of logits
+            -> row LSE (complete) + column (max, sum-exp) partials -> all_reduce -> both CE losses
+  backward  d(words) complete locally;  d(regions) partial for all B images -> reduce_scatter.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .engine import get_engine
+
+DEFAULT_GAMMAS = (4.0, 5.0, 10.0)      # cfg/DAMSM/bird.yml:27-29, coco.yml:27-29, clip_bird_DMGAN.yml:25-28
+
+
+# ----------------------------------------------------------------------------------------------- collectives
+def _world(group):
+    if group is None:
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def _all_gather_rows(x: torch.Tensor, group):
+    """Concatenate equal-sized row shards from every rank (rank order)."""
+    if group is None:
+        return x
+    world = dist.get_world_size(group)
+    x = x.contiguous()
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+    dist.all_gather_into_tensor(out, x, group=group)
+    return out
+
+
+def _reduce_scatter_rows(x: torch.Tensor, group):
+    """Sum ``x`` (B_total, ...) over ranks and return this rank's row shard."""
+    if group is None:
+        return x
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    x = x.contiguous()
+    rows = x.shape[0] // world
+    if dist.get_backend(group) == "gloo":          # gloo has no reduce_scatter
+        dist.all_reduce(x, group=group)
+        return x[rank * rows:(rank + 1) * rows].clone()
+    out = torch.empty((rows,) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+    dist.reduce_scatter_tensor(out, x, group=group)
+    return out
+
+
+def combine_column_lse(col_max: torch.Tensor, col_sum: torch.Tensor, group):
+    """Column log-sum-exp of the full (B x B) matrix from per-rank (max, sum exp(x-max)) partials."""
+    if group is None:
+        return torch.log(col_sum) + col_max
+    gmax = col_max.clone()
+    dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
+    scale = torch.where(col_max == gmax, torch.ones_like(col_max), torch.exp(col_max - gmax))
+    s = col_sum * scale
+    dist.all_reduce(s, group=group)
+    return torch.log(s) + gmax
+
+
+# ----------------------------------------------------------------------------------------------- words loss
+class DamsmWordsLoss(torch.autograd.Function):
+    """words_loss (losses.py:219-272) for the local caption rows against all images."""
+
+    @staticmethod
+    def forward(ctx, regions3, words3, mask_u8, labels, cls_local, gammas, engine, group):
+        world, rank = _world(group)
+        bl = words3.shape[0]
+        if regions3.shape[0] != bl:
+            raise ValueError("words and regions must have the same (local) batch size")
+        b_total, row_offset = bl * world, rank * bl
+        qhat, qhat16, qnorm, qunorm = engine.l2norm_fwd(words3, want_bf16=engine.precision == "bf16")
+        vhat_l, vhat16_l, vnorm, _ = engine.l2norm_fwd(regions3, want_bf16=engine.precision == "bf16")
+        vhat = _all_gather_rows(vhat_l, group)
+        cls_all = _all_gather_rows(cls_local, group) if cls_local is not None else None
+        colside = engine.words_prepare_columns(vhat)
+        sim = engine.words_fwd(qhat, vhat, colside, qunorm, mask_u8, gammas)
+        row_lse, col_max, col_sum = engine.ce_stats(sim, cls_local, cls_all, row_offset)
+        col_lse = combine_column_lse(col_max, col_sum, group)
+        out2 = engine.ce_losses(sim, row_lse, col_lse, labels, row_offset, b_total)
+        if group is not None:
+            dist.all_reduce(out2, group=group)
+        ctx.engine, ctx.group, ctx.gammas = engine, group, gammas
+        ctx.row_offset, ctx.b_total = row_offset, b_total
+        ctx.save_for_backward(regions3, words3, mask_u8, labels, qhat, vhat, colside, qnorm, qunorm, vnorm,
+                              sim, row_lse, col_lse)
+        ctx.mark_non_differentiable(sim)
+        return out2[0].clone(), out2[1].clone(), sim
+
+    @staticmethod
+    def backward(ctx, g0, g1, _gsim):
+        (regions3, words3, mask_u8, labels, qhat, vhat, colside, qnorm, qunorm, vnorm,
+         sim, row_lse, col_lse) = ctx.saved_tensors
+        eng = ctx.engine
+        gscale = torch.stack([g0.reshape(()), g1.reshape(())]).to(torch.float32)
+        dqhat, dvhat, kq = eng.words_bwd(qhat, vhat, colside, qunorm, mask_u8, sim, row_lse, col_lse, labels,
+                                         gscale, ctx.row_offset, ctx.b_total, ctx.gammas)
+        dregions3 = dwords3 = None
+        if ctx.needs_input_grad[0]:
+            dvhat_l = _reduce_scatter_rows(dvhat, ctx.group)
+            dregions3 = eng.l2norm_bwd(regions3, vnorm, dvhat_l, None)
+        if ctx.needs_input_grad[1]:
+            dwords3 = eng.l2norm_bwd(words3, qnorm, dqhat, kq)
+        return dregions3, dwords3, None, None, None, None, None, None
+
+
+class LazyAttnMaps:
+    """Stands in for the reference's ``attn_maps`` (losses.py:249): a list of B tensors (B, R, T) with the
+    softmax-over-words probabilities of caption i against every image.  The reference materialises
+    O(B^2 R T) floats whose only consumers are commented out (pretrain_DAMSM.py:221-228,
+    trainer.py:446-453); here entry i is computed on first access."""
+
+    def __init__(self, words3, regions3, mask_u8, engine):
+        self._w, self._r, self._m, self._e = words3.detach(), regions3.detach(), mask_u8, engine
+        self._cache = {}
+
+    def __len__(self):
+        return self._w.shape[0]
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        if i not in self._cache:
+            b = self._r.shape[0]
+            qhat, _, _, _ = self._e.l2norm_fwd(self._w[i:i + 1])
+            vhat, _, _, _ = self._e.l2norm_fwd(self._r)
+            q = qhat.expand(b, -1, -1).contiguous()
+            m = self._m[i:i + 1].expand(b, -1).contiguous()
+            _, attn, _ = self._e.func_attention_fwd(q, vhat, vhat, m, 1.0)
+            self._cache[i] = attn.transpose(1, 2)            # (B, R, T) like losses.py:143-144
+        return self._cache[i]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+def _as_bnd(x: torch.Tensor, what: str):
+    """(B, D, N) or (B, D, h, w) reference layout -> (B, N, D) strided view (no copy when possible)."""
+    if x.dim() == 4:                                      # losses.py:350 hands over (B, 512, 7, 7)
+        x = x.flatten(2)
+    if x.dim() != 3:
+        raise ValueError(f"{what} must be (B, D, N) or (B, D, h, w); got {tuple(x.shape)}")
+    return x.permute(0, 2, 1)
+
+
+def _mask_to_u8(words_mask, cap_lens, b, t, device):
+    if words_mask is None:                                # stale 6-argument call sites (losses.py:352, trainer.py:235)
+        if cap_lens is None:
+            return torch.ones((b, t), dtype=torch.uint8, device=device)
+        cl = torch.as_tensor(cap_lens).to(device=device, dtype=torch.int64).reshape(b, 1)
+        return (torch.arange(t, device=device).reshape(1, t) < cl).to(torch.uint8)
+    m = torch.as_tensor(words_mask)
+    if m.dim() == 3:
+        m = m.reshape(m.shape[0], -1)
+    if tuple(m.shape) != (b, t):
+        raise ValueError(f"words_mask must be ({b}, {t}); got {tuple(m.shape)}")
+    return (m.to(device=device, non_blocking=True) != 0).to(torch.uint8).contiguous()
+
+
+def _class_ids_tensor(class_ids, b, device):
+    if class_ids is None:
+        return None
+    c = torch.as_tensor(np.asarray(class_ids) if not torch.is_tensor(class_ids) else class_ids)
+    c = c.reshape(-1).to(device=device, dtype=torch.int64)
+    if c.numel() != b:
+        raise ValueError(f"class_ids must have {b} entries; got {c.numel()}")
+    return c
+
+
+def _pick_precision(precision, *tensors):
+    if precision is not None:
+        return precision
+    return "fp32"
+
+
+def words_loss(region_features, words_embs, match_labels, cap_lens, class_ids, batch_size,
+               words_mask=None, gamma1=None, gamma2=None, gamma3=None, *, precision=None, group=None,
+               engine=None):
+    """Drop-in for ``miscc.losses.words_loss`` (losses.py:219).  Same positional signature, including the
+    stale 6-argument form.  Extra keyword-only arguments: ``precision`` ('fp32' exact SIMT path, 'bf16'
+    tcgen05 path), ``group`` (a torch.distributed process group: inputs are then this rank's shard of the
+    batch and every rank's images serve as negatives), ``engine`` (tests only).
+
+    Returns ``(loss0, loss1, attn_maps)``; ``match_labels=None`` gives ``(None, None, attn_maps)``.
+    """
+    regions3 = _as_bnd(region_features, "region_features")
+    words3 = _as_bnd(words_embs, "words_embs")
+    b, t, d = words3.shape
+    if batch_size is not None and int(batch_size) != b:
+        raise ValueError(f"batch_size={batch_size} does not match the tensors' batch {b}")
+    if regions3.shape[2] != d:
+        raise ValueError("words and regions must share the embedding size")
+    eng = engine or get_engine(_pick_precision(precision, words3, regions3))
+    dev = words3.device
+    mask_u8 = _mask_to_u8(words_mask, cap_lens, b, t, dev)
+    attn_maps = LazyAttnMaps(words3, regions3, mask_u8, eng)
+    if match_labels is None:
+        return None, None, attn_maps
+    gammas = (DEFAULT_GAMMAS[0] if gamma1 is None else float(gamma1),
+              DEFAULT_GAMMAS[1] if gamma2 is None else float(gamma2),
+              DEFAULT_GAMMAS[2] if gamma3 is None else float(gamma3))
+    world, _ = _world(group)
+    labels = torch.as_tensor(match_labels).to(device=dev, dtype=torch.int64).contiguous()
+    if labels.numel() != b * world:
+        raise ValueError(f"match_labels must have {b * world} entries (global batch)")
+    cls = _class_ids_tensor(class_ids, b, dev)
+    loss0, loss1, _ = DamsmWordsLoss.apply(regions3, words3, mask_u8, labels, cls, gammas, eng, group)
+    return loss0, loss1, attn_maps
+
+
+# ----------------------------------------------------------------------------------------------- sentence loss
+class DamsmSentLoss(torch.autograd.Function):
+    """sent_loss (losses.py:51-91): rows = local image codes, columns = all caption codes."""
+
+    @staticmethod
+    def forward(ctx, img, txt, labels, cls_local, gamma3, eps, engine, group):
+        world, rank = _world(group)
+        bl = img.shape[0]
+        b_total, row_offset = bl * world, rank * bl
+        img = img.contiguous()
+        txt_all = _all_gather_rows(txt.contiguous(), group)
+        cls_all = _all_gather_rows(cls_local, group) if cls_local is not None else None
+        logits, na, nb = engine.cos_logits(img, txt_all, gamma3, eps)
+        row_lse, col_max, col_sum = engine.ce_stats(logits, cls_local, cls_all, row_offset)
+        col_lse = combine_column_lse(col_max, col_sum, group)
+        out2 = engine.ce_losses(logits, row_lse, col_lse, labels, row_offset, b_total)
+        if group is not None:
+            dist.all_reduce(out2, group=group)
+        ctx.engine, ctx.group, ctx.gamma3, ctx.eps = engine, group, gamma3, eps
+        ctx.row_offset, ctx.b_total = row_offset, b_total
+        ctx.save_for_backward(img, txt_all, labels, na, nb, logits, row_lse, col_lse)
+        return out2[0].clone(), out2[1].clone()
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        img, txt_all, labels, na, nb, logits, row_lse, col_lse = ctx.saved_tensors
+        gscale = torch.stack([g0.reshape(()), g1.reshape(())]).to(torch.float32)
+        da, db = ctx.engine.cos_logits_bwd(img, txt_all, na, nb, logits, row_lse, col_lse, labels, gscale,
+                                           ctx.row_offset, ctx.b_total, ctx.gamma3, ctx.eps)
+        dtxt = _reduce_scatter_rows(db, ctx.group) if ctx.needs_input_grad[1] else None
+        return (da if ctx.needs_input_grad[0] else None), dtxt, None, None, None, None, None, None
+
+
+def sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, eps=1e-8, *, gamma3=None, group=None,
+              engine=None):
+    """Drop-in for ``miscc.losses.sent_loss`` (losses.py:51).  ``gamma3`` defaults to the cfg value the
+    reference reads at losses.py:79 (10.0 in every shipped yml)."""
+    if cnn_code.dim() == 3:                                # (1, B, D) as produced by losses.py:69-71
+        if cnn_code.shape[0] != 1:
+            raise ValueError("sent_loss: only seq_len == 1 is meaningful (losses.py:82 squeezes it away)")
+        cnn_code, rnn_code = cnn_code[0], rnn_code[0]
+    if cnn_code.dim() != 2 or rnn_code.shape != cnn_code.shape:
+        raise ValueError("sent_loss: cnn_code and rnn_code must both be (B, D)")
+    b = cnn_code.shape[0]
+    if batch_size is not None and int(batch_size) != b:
+        raise ValueError(f"batch_size={batch_size} does not match the tensors' batch {b}")
+    if labels is None:
+        return None, None
+    eng = engine or get_engine("fp32")
+    dev = cnn_code.device
+    world, _ = _world(group)
+    lab = torch.as_tensor(labels).to(device=dev, dtype=torch.int64).contiguous()
+    if lab.numel() != b * world:
+        raise ValueError(f"labels must have {b * world} entries (global batch)")
+    cls = _class_ids_tensor(class_ids, b, dev)
+    g3 = DEFAULT_GAMMAS[2] if gamma3 is None else float(gamma3)
+    out_dtype = cnn_code.dtype
+    l0, l1 = DamsmSentLoss.apply(cnn_code.float(), rnn_code.float(), lab, cls, g3, float(eps), eng, group)
+    return l0.to(out_dtype) if out_dtype != torch.float32 else l0, l1.to(out_dtype) if out_dtype != torch.float32 else l1
+
+
+# ----------------------------------------------------------------------------------------------- func_attention
+class DamsmFuncAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, query3, context3, mask_u8, gamma1, engine):
+        qhat, _, qnorm, _ = engine.l2norm_fwd(query3)
+        vhat, _, vnorm, _ = engine.l2norm_fwd(context3)
+        ctx32 = context3 if context3.dtype == torch.float32 else context3.float()
+        wc, attn, attn2 = engine.func_attention_fwd(qhat, vhat, ctx32, mask_u8, gamma1)
+        ctx.engine, ctx.gamma1 = engine, gamma1
+        ctx.save_for_backward(query3, context3, ctx32, qhat, vhat, qnorm, vnorm, attn, attn2)
+        return wc, attn
+
+    @staticmethod
+    def backward(ctx, d_wc, d_attn):
+        query3, context3, ctx32, qhat, vhat, qnorm, vnorm, attn, attn2 = ctx.saved_tensors
+        eng = ctx.engine
+        d_wc = d_wc.contiguous().float() if d_wc is not None else None
+        d_attn = d_attn.contiguous().float() if d_attn is not None else None
+        dqhat, dvhat, dctx = eng.func_attention_bwd(qhat, vhat, ctx32, attn, attn2, d_wc, d_attn, ctx.gamma1)
+        dq = eng.l2norm_bwd(query3, qnorm, dqhat, None) if ctx.needs_input_grad[0] else None
+        dc = None
+        if ctx.needs_input_grad[1]:
+            dc = eng.l2norm_bwd(context3, vnorm, dvhat, None) + dctx.to(context3.dtype)
+        return dq, dc, None, None, None
+
+
+def func_attention(query, context, gamma1, query_mask, *, engine=None):
+    """Drop-in for ``GlobalAttention.func_attention`` (GlobalAttention.py:38).
+
+    query (B, D, T), context (B, D, R) with R a perfect square (:54), query_mask (B, 1, T).
+    Returns (weightedContext (B, T, D), attn (B, T, sqrt R, sqrt R))."""
+    if query.dim() != 3 or context.dim() != 3:
+        raise ValueError("func_attention: query must be (B, D, T) and context (B, D, R)")
+    b, d, t = query.shape
+    r = context.shape[2]
+    side = int(math.sqrt(r))
+    if side * side != r:
+        raise ValueError(f"func_attention: number of regions {r} is not a perfect square (GlobalAttention.py:54,156)")
+    eng = engine or get_engine("fp32")
+    m = torch.as_tensor(query_mask)
+    mask_u8 = (m.reshape(b, t).to(query.device) != 0).to(torch.uint8).contiguous()
+    wc, attn = DamsmFuncAttention.apply(query.permute(0, 2, 1), context.permute(0, 2, 1), mask_u8, float(gamma1), eng)
+    if query.dtype != torch.float32:
+        wc, attn = wc.to(query.dtype), attn.to(query.dtype)
+    return wc, attn.view(b, t, side, side)
