@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""DAMSM words_loss + sent_loss forward+backward throughput (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c5|...] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path -- words_loss + sent_loss forward
+and backward (gradients to words, regions, sentence and image codes) -- over one batch of synthetic
+input (SURVEY.md 8d generator).  ``value`` = matched caption-image pairs/s with the inputs already in HBM;
+``e2e`` = the same through the public drop-in API with pinned host inputs copied to the device and the
+losses read back every step.  For N>1 launch with torchrun (one rank per GPU, NCCL); the global batch is
+fixed and sharded by caption rows (strong scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+GAMMAS = (4.0, 5.0, 10.0)
+D = 512
+# BASELINE.json configs[0..4]
+WORKLOADS = {
+    "c1": dict(B=48, T=18, R=49, cls=True, precision="fp32", seed=2026, desc="CUB bird DAMSM shape"),
+    "c2": dict(B=48, T=18, R=49, cls=False, precision="fp32", seed=2027, desc="COCO DAMSM shape, class mask off"),
+    "c3": dict(B=10, T=77, R=49, cls=True, precision="fp32", seed=2028, desc="DM-GAN generator-step DAMSM term"),
+    "c4": dict(B=1024, T=77, R=196, cls=False, precision="bf16", seed=2029, desc="large-batch fine-tune, ViT-B/16"),
+    "c5": dict(B=4096, T=77, R=196, cls=False, precision="bf16", seed=2030, desc="scaling sweep, ViT-B/16, bf16 in"),
+}
+
+
+def algorithmic_flops(B, T, R):
+    """12*B^2*T*R*D + 6*B^2*D per fwd+bwd step (no recompute, no padding counted)."""
+    return 12.0 * B * B * T * R * D + 6.0 * B * B * D
+
+
+def make_inputs(w, dtype):
+    """Seeded synthetic batch, generated with torch on the host."""
+    B, T, R = w["B"], w["T"], w["R"]
+    g = torch.Generator().manual_seed(w["seed"])
+    s = torch.randn(B, 1, D, generator=g)
+    words = (0.25 * s + torch.randn(B, T, D, generator=g)).to(dtype)
+    regions = (0.25 * s + torch.randn(B, R, D, generator=g)).to(dtype)
+    sent = (0.25 * s[:, 0] + torch.randn(B, D, generator=g)).to(dtype)
+    img = (0.25 * s[:, 0] + torch.randn(B, D, generator=g)).to(dtype)
+    lo = max(2, T // 3)
+    cap_len = torch.randint(lo, T + 1, (B,), generator=g)
+    mask = (torch.arange(T).reshape(1, T) < cap_len.reshape(B, 1)).to(torch.int64)
+    cls = torch.randint(0, 200, (B,), generator=g).numpy() if w["cls"] else None
+    return dict(words=words, regions=regions, sent=sent, img=img, mask=mask, cap_len=cap_len, class_ids=cls)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [v.strip() for v in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            # "under load": samples in the upper half of the power range
+            thr = 0.5 * (max(power) + min(power))
+            load = [s for s, p in zip(sm, power) if p >= thr] or sm
+            out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(power)))
+        return out
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return world, rank, local, dist.group.WORLD
+    if n_gpus > 1:
+        raise SystemExit("for --gpus N>1 launch with: python -m torch.distributed.run --nproc-per-node N bench.py ...")
+    torch.cuda.set_device(0)
+    return 1, 0, 0, None
+
+
+def max_over_ranks(x, group):
+    if group is None:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
+
+
+def barrier(group):
+    if group is not None:
+        import torch.distributed as dist
+        dist.barrier(group=group)
+    torch.cuda.synchronize()
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, w):
+    """The reference's own CPU procedure (oracle/ref_port.py: the reference is pure Python and does not
+    travel to the GPU box) on the host cores, on a bounded sample of the workload."""
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = w["B"]
+    Bs = B if B <= 64 else 32          # bounded sample: the reference is O(B^2) time and O(B^2 R D) memory
+    ws = dict(w, B=Bs)
+    x = make_inputs(ws, torch.float32)
+    xin = {k: (v.numpy() if torch.is_tensor(v) else v) for k, v in x.items()}
+    xin["labels"] = np.arange(Bs)
+    for _ in range(max(1, min(args.warmup, 1))):
+        ref_port.step(xin, GAMMAS)
+    ts = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        ref_port.step(xin, GAMMAS)
+        ts.append(time.perf_counter() - t0)
+    t_sample = float(np.median(ts))
+    t_full = t_sample * (B / Bs) ** 2   # time grows with the number of scored pairs
+    value = B / t_full
+    sample = (f"{Bs}x{Bs} pairs of the workload (T={w['T']}, R={w['R']}, fp32), words_loss+sent_loss fwd+bwd, "
+              f"median of {args.steps}; " + ("full size" if Bs == B else f"extrapolated to B={B} with time ~ B^2"))
+    line = dict(metric="damsm_fwd_bwd_matched_pairs_per_s", value=value, unit="caption-image pairs/s", impl="reference",
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=t_full * 1e3,
+                higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=args.workload, B=B, T=w["T"], R=w["R"], D=D, description=w["desc"]),
+                cpu_baseline=dict(value=value, unit="caption-image pairs/s", cores=cores, kind="port", sample=sample,
+                                  measured_ms_per_sample_step=t_sample * 1e3, sample_batch=Bs),
+                e2e=dict(value=value, unit="caption-image pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=None, choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    pkg = importlib.import_module("t2i_clip-gan_b200")
+    has_tc = args.impl == "ours" and hasattr(pkg._lib.load(), "damsm_words_fwd_bf16")
+    if args.workload is None:
+        args.workload = "c5" if has_tc else "c2"
+    w = dict(WORKLOADS[args.workload])
+    if args.precision:
+        w["precision"] = args.precision
+    if args.steps is None:
+        args.steps = 5 if w["B"] >= 1024 else 20
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_reference(args, w)
+        return
+
+    world, rank, local, group = dist_setup(args.gpus)
+    B, T, R = w["B"], w["T"], w["R"]
+    assert B % world == 0, "global batch must divide by the number of GPUs"
+    bl = B // world
+    lo, hi = rank * bl, (rank + 1) * bl
+    in_dtype = torch.bfloat16 if w["precision"] == "bf16" else torch.float32
+    x = make_inputs(w, in_dtype)
+    host = {k: x[k][lo:hi].contiguous().pin_memory() for k in ("words", "regions", "sent", "img", "mask")}
+    cls_local = x["class_ids"][lo:hi] if x["class_ids"] is not None else None
+    labels = torch.arange(B, device="cuda")
+    cap_len = x["cap_len"][lo:hi]
+    prec = w["precision"]
+
+    def step(dev):
+        """One pass of the hot path through the public drop-in API (reference call shapes)."""
+        words = dev["words"].permute(0, 2, 1)          # (B, D, T) view, pretrain_DAMSM.py:130
+        regions = dev["regions"].permute(0, 2, 1)      # (B, D, R) view, pretrain_DAMSM.py:125
+        w0, w1, _ = pkg.words_loss(regions, words, labels, cap_len, cls_local, bl, dev["mask"], *GAMMAS,
+                                   precision=prec, group=group)
+        s0, s1 = pkg.sent_loss(dev["img"], dev["sent"], labels, cls_local, bl, gamma3=GAMMAS[2], group=group)
+        loss = w0 + w1 + s0.float() + s1.float()
+        loss.backward()
+        return torch.stack([w0.detach(), w1.detach(), s0.detach().float(), s1.detach().float()])
+
+    def to_device(non_blocking=True):
+        dev = {k: host[k].to("cuda", non_blocking=non_blocking) for k in host}
+        for k in ("words", "regions", "sent", "img"):
+            dev[k].requires_grad_(True)
+        return dev
+
+    # ---- device-resident arm: inputs already in HBM -----------------------------------------------------------
+    dev = to_device(False)
+    in_bytes = sum(host[k].numel() * host[k].element_size() for k in host)
+    flush = None
+    l2_note = "inputs larger than L2 (no flush)"
+    if in_bytes * world < 200e6:                     # small workloads: flush the 126 MB L2 between iterations
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+        l2_note = "L2 flushed (256 MiB memset) between timed iterations"
+
+    def clear_grads():
+        for k in ("words", "regions", "sent", "img"):
+            dev[k].grad = None
+
+    for _ in range(args.warmup):
+        clear_grads()
+        losses = step(dev)
+    barrier(group)
+    pkg._lib.reset_launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    evs = []
+    barrier(group)
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        clear_grads()
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        losses = step(dev)
+        e1.record()
+        evs.append((e0, e1))
+    barrier(group)
+    t_wall = time.perf_counter() - t_wall0
+    launches = pkg._lib.launch_count()
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    ms_total = max_over_ranks(ms_total, group)
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = B / (ms_step * 1e-3)
+    loss_vals = [float(v) for v in losses.cpu()]
+
+    # ---- end-to-end arm: pinned host inputs -> device every step, losses read back every step -------------------
+    h2d = sum(host[k].numel() * host[k].element_size() for k in host)
+    d2h = 4 * 4
+    out_pinned = torch.empty(4, dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        dev2 = to_device()
+        out_pinned.copy_(step(dev2))
+    barrier(group)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dev2 = to_device()
+        out_pinned.copy_(step(dev2), non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the caller reads the loss (pretrain_DAMSM.py:138-160)
+    barrier(group)
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps, group)
+    e2e = dict(value=B / e2e_s, unit="caption-image pairs/s", ms_per_step=e2e_s * 1e3,
+               h2d_bytes_per_step=int(h2d * world), d2h_bytes_per_step=int(d2h * world))
+
+    # ---- roofline of the dominant kernels, timed alone with CUDA events on the launching stream ------------------
+    roof = measure_roofline(pkg, w, dev, bl, B, rank, group, prec)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = measure_cpu_baseline(w)
+
+    if rank == 0:
+        line = dict(metric="damsm_fwd_bwd_matched_pairs_per_s", value=value, unit="caption-image pairs/s",
+                    n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
+                    higher_is_better=True, scaling="strong", vs_baseline=None,
+                    dtype="bf16 operands / f32 accumulate" if prec == "bf16" else "f32", data="synthetic",
+                    config=dict(workload=args.workload, description=w["desc"], global_batch=B, local_batch=bl,
+                                T=T, R=R, D=D, class_mask=bool(w["cls"]), gammas=list(GAMMAS), precision=prec,
+                                parallelism=f"caption-row shards x{world}" if world > 1 else "single GPU",
+                                l2=l2_note, step="words_loss + sent_loss forward + backward, grads to all 4 inputs"),
+                    scored_pairs_per_s=B * B / (ms_step * 1e-3),
+                    algorithmic_tflops=algorithmic_flops(B, T, R) / (ms_step * 1e-3) / 1e12,
+                    losses=loss_vals, wall_ms_per_step=t_wall / args.steps * 1e3,
+                    clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu_base)
+        print(json.dumps(line))
+    if group is not None:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained"), hbm=d["hbm_gbs"], src="measured")
+    return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+def measure_roofline(pkg, w, dev, bl, B, rank, group, prec):
+    """Time the dominant kernel (the fused word/region pair kernels, forward + backward launches) alone.
+    achieved = algorithmic flops of those launches / their measured duration; peak = measured bf16 dense."""
+    eng = pkg.get_engine(prec)
+    T, R = w["T"], w["R"]
+    peaks = load_peaks()
+    with torch.no_grad():
+        words3, regions3 = dev["words"].detach(), dev["regions"].detach()
+        qhat, qhat16, qnorm, qunorm = eng.l2norm_fwd(words3, want_bf16=prec == "bf16")
+        vhat_l, _, vnorm, _ = eng.l2norm_fwd(regions3, want_bf16=prec == "bf16")
+        vhat = pkg.ops._all_gather_rows(vhat_l, group)
+        mask_u8 = (dev["mask"] != 0).to(torch.uint8).contiguous()
+        col = eng.words_prepare_columns(vhat)
+        sim = eng.words_fwd(qhat, vhat, col, qunorm, mask_u8, GAMMAS)
+        row_lse, cmax, csum = eng.ce_stats(sim, None, None, rank * bl)
+        col_lse = pkg.combine_column_lse(cmax, csum, group)
+        gscale = torch.ones(2, device="cuda")
+        labels = torch.arange(B, device="cuda")
+        reps = 3 if B >= 1024 else 10
+
+        def timed(fn):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        t_f = timed(lambda: eng.words_fwd(qhat, vhat, col, qunorm, mask_u8, GAMMAS))
+        t_b = timed(lambda: eng.words_bwd(qhat, vhat, col, qunorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
+                                          rank * bl, B, GAMMAS))
+    f_fwd = 4.0 * bl * B * T * R * D
+    f_bwd = 8.0 * bl * B * T * R * D
+    ach = (f_fwd + f_bwd) / ((t_f + t_b) * 1e-3) / 1e12
+    return dict(bound="tensor", achieved=ach, peak=peaks["bf16"], unit="TFLOP/s", frac=ach / peaks["bf16"],
+                traffic=None, peak_source=peaks["src"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
+                kernel="words pair kernels (fwd launch + bwd launch), algorithmic flops 4+8 * B_rows*B*T*R*D",
+                fwd_ms=t_f, bwd_ms=t_b, fwd_tflops=f_fwd / (t_f * 1e-3) / 1e12, bwd_tflops=f_bwd / (t_b * 1e-3) / 1e12,
+                note=("exact fp32 SIMT path: the tensor roofline is quoted for comparison only; this configuration is "
+                      "latency-bound (SURVEY 8d)") if prec == "fp32" else "bf16 tcgen05 path")
+
+
+def measure_cpu_baseline(w):
+    """oracle/ref_port.py (procedure port of the reference) on this box's host cores, bounded sample."""
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = w["B"]
+    Bs = B if B <= 64 else 32
+    ws = dict(w, B=Bs)
+    x = make_inputs(ws, torch.float32)
+    xin = {k: (v.numpy() if torch.is_tensor(v) else v) for k, v in x.items()}
+    xin["labels"] = np.arange(Bs)
+    ref_port.step(xin, GAMMAS)
+    ts = []
+    t_budget = time.perf_counter() + 20.0
+    while len(ts) < 5 and (time.perf_counter() < t_budget or len(ts) < 2):
+        t0 = time.perf_counter()
+        ref_port.step(xin, GAMMAS)
+        ts.append(time.perf_counter() - t0)
+    t_sample = float(np.median(ts))
+    t_full = t_sample * (B / Bs) ** 2
+    return dict(value=B / t_full, unit="caption-image pairs/s", cores=cores, kind="port",
+                sample=(f"{Bs}x{Bs} pairs (T={w['T']}, R={w['R']}, fp32) fwd+bwd, median of {len(ts)}; "
+                        + ("full size" if Bs == B else f"extrapolated to B={B} with time ~ B^2")),
+                measured_ms_per_sample_step=t_sample * 1e3, sample_batch=Bs)
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,15 @@ SIGNATURES = {
 }
 _RESTYPE = {"damsm_last_error": C.c_char_p, "damsm_words_f32_smem_bytes": C.c_int64}
 
+# kernels launched per successful call of each entry point (bench.py reports the total as gpu_launches)
+LAUNCHES = {
+    "damsm_l2norm_fwd": 1, "damsm_l2norm_bwd": 1, "damsm_gram_f32": 1, "damsm_gram_bwd_f32": 1,
+    "damsm_words_fwd_f32": 1, "damsm_words_bwd_f32": 1, "damsm_ce_stats_f32": 2, "damsm_ce_losses_f32": 1,
+    "damsm_cos_logits_f32": 4, "damsm_cos_logits_bwd_f32": 5,
+    "damsm_func_attention_fwd_f32": 1, "damsm_func_attention_bwd_f32": 1,
+}
+_launches = 0
+
 _lib = None
 
 
@@ -79,10 +88,21 @@ def load():
 
 def call(name: str, *args):
     """Call an int-returning entry point and raise on a non-zero status."""
+    global _launches
     lib = load()
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise DamsmError(f"{name} failed ({rc}): {lib.damsm_last_error().decode(errors='replace')}")
+    _launches += LAUNCHES.get(name, 0)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def reset_launch_count() -> None:
+    global _launches
+    _launches = 0
 
 
 def ptr(t):
