@@ -338,11 +338,12 @@ def measure_roofline(pkg, w, dev, bl, B, rank, group, prec):
     with torch.no_grad():
         words3, regions3 = dev["words"].detach(), dev["regions"].detach()
         qhat, qhat16, qnorm, qunorm = eng.l2norm_fwd(words3, want_bf16=prec == "bf16")
-        vhat_l, _, vnorm, _ = eng.l2norm_fwd(regions3, want_bf16=prec == "bf16")
+        vhat_l, vhat16_l, vnorm, _ = eng.l2norm_fwd(regions3, want_bf16=prec == "bf16")
         vhat = pkg.ops._all_gather_rows(vhat_l, group)
         mask_u8 = (dev["mask"] != 0).to(torch.uint8).contiguous()
-        col = eng.words_prepare_columns(vhat)
-        sim = eng.words_fwd(qhat, vhat, col, qunorm, mask_u8, GAMMAS)
+        vhat16 = pkg.ops._all_gather_rows(vhat16_l, group) if vhat16_l is not None else None
+        col = eng.words_prepare_columns(vhat, vhat16)
+        sim = eng.words_fwd(qhat, qhat16, vhat, col, qunorm, mask_u8, GAMMAS)
         row_lse, cmax, csum = eng.ce_stats(sim, None, None, rank * bl)
         col_lse = pkg.combine_column_lse(cmax, csum, group)
         gscale = torch.ones(2, device="cuda")
@@ -360,8 +361,8 @@ def measure_roofline(pkg, w, dev, bl, B, rank, group, prec):
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / reps
 
-        t_f = timed(lambda: eng.words_fwd(qhat, vhat, col, qunorm, mask_u8, GAMMAS))
-        t_b = timed(lambda: eng.words_bwd(qhat, vhat, col, qunorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
+        t_f = timed(lambda: eng.words_fwd(qhat, qhat16, vhat, col, qunorm, mask_u8, GAMMAS))
+        t_b = timed(lambda: eng.words_bwd(qhat, qhat16, vhat, col, qunorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
                                           rank * bl, B, GAMMAS))
     f_fwd = 4.0 * bl * B * T * R * D
     f_bwd = 8.0 * bl * B * T * R * D

@@ -94,6 +94,19 @@ DAMSM_API int damsm_words_bwd_f32(const float *qhat, const float *vhat, const fl
 /* host: dynamic shared memory the fused fp32 pair kernel needs for (T,R); <0 if unsupported */
 DAMSM_API int64_t damsm_words_f32_smem_bytes(int64_t t, int64_t r);
 
+/* ---- bf16 tensor-core path (tcgen05 / TMEM / TMA), same math as damsm_words_fwd_f32 ---------------------
+ * qhat16 (br,T,D), vhat16 (bc,R,D): bf16 copies of the normalised embeddings (damsm_l2norm_fwd).
+ * gx (bc, R+1, RK) bf16 with RK = damsm_words_tc_gx_cols(R): the Gram matrix of each image, columns
+ * zero-padded to a multiple of 64, plus one appended row of ones (it makes the second GEMM deliver the
+ * softmax-over-regions denominators).  Parity target: rel <= 2e-3 against the fp32 reference. */
+DAMSM_API int64_t damsm_words_tc_gx_cols(int64_t r);
+DAMSM_API int damsm_gram_pack_bf16(const float *gram, int64_t bc, int64_t r, void *gx, void *stream);
+/* host: dynamic shared memory of the tcgen05 kernel for (T,R,D); <0 if the shape is unsupported */
+DAMSM_API int64_t damsm_words_tc_smem_bytes(int64_t t, int64_t r, int64_t d);
+DAMSM_API int damsm_words_fwd_bf16(const void *qhat16, const void *vhat16, const void *gx, const float *unorm,
+                                   const uint8_t *mask, int64_t br, int64_t bc, int64_t t, int64_t r, int64_t d,
+                                   float gamma1, float gamma2, float gamma3, float *sim, void *stream);
+
 /* ---- class_ids masking + both CrossEntropyLoss() (losses.py:55-66,84-88 / :224-232,256-269) -----------
  * logits (br,bc) row block of the (b_total x b_total) matrix.  In place: logits[i][j] = -inf where
  * cls_rows[i]==cls_cols[j] and j != row_offset+i (cls_* may be NULL = no masking).

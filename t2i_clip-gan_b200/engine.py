@@ -68,26 +68,40 @@ class CudaEngine:
         return dx
 
     # ---- word / region scores ---------------------------------------------------------------------------
-    def words_prepare_columns(self, vhat: torch.Tensor):
-        """Per-image side data derived from vhat (bc,R,D): the Gram matrices."""
+    def words_prepare_columns(self, vhat: torch.Tensor, vhat16=None):
+        """Per-image side data derived from vhat (bc,R,D): the Gram matrices (fp32) and, for the
+        tensor-core path, their padded bf16 form with the appended row of ones."""
         bc, r, d = vhat.shape
         gram = torch.empty((bc, r, r), device=vhat.device, dtype=torch.float32)
         _lib.call("damsm_gram_f32", vhat.data_ptr(), bc, r, d, gram.data_ptr(), _stream())
-        return gram
+        col = {"gram": gram}
+        if self.precision == "bf16":
+            rk = _lib.load().damsm_words_tc_gx_cols(r)
+            gx = torch.empty((bc, r + 1, rk), device=vhat.device, dtype=torch.bfloat16)
+            _lib.call("damsm_gram_pack_bf16", gram.data_ptr(), bc, r, gx.data_ptr(), _stream())
+            col["gx"] = gx
+            col["vhat16"] = vhat16
+        return col
 
-    def words_fwd(self, qhat, vhat, gram, unorm, mask_u8, gammas):
-        _require_cuda(qhat, vhat, gram, unorm, mask_u8)
+    def words_fwd(self, qhat, qhat16, vhat, col, unorm, mask_u8, gammas):
+        _require_cuda(qhat, vhat, unorm, mask_u8)
         br, t, d = qhat.shape
         bc, r, _ = vhat.shape
         sim = torch.empty((br, bc), device=qhat.device, dtype=torch.float32)
-        _lib.call("damsm_words_fwd_f32", qhat.data_ptr(), vhat.data_ptr(), gram.data_ptr(), unorm.data_ptr(),
-                  mask_u8.data_ptr(), br, bc, t, r, d, float(gammas[0]), float(gammas[1]), float(gammas[2]),
-                  sim.data_ptr(), _stream())
+        if self.precision == "bf16":
+            _lib.call("damsm_words_fwd_bf16", qhat16.data_ptr(), col["vhat16"].data_ptr(), col["gx"].data_ptr(),
+                      unorm.data_ptr(), mask_u8.data_ptr(), br, bc, t, r, d,
+                      float(gammas[0]), float(gammas[1]), float(gammas[2]), sim.data_ptr(), _stream())
+        else:
+            _lib.call("damsm_words_fwd_f32", qhat.data_ptr(), vhat.data_ptr(), col["gram"].data_ptr(),
+                      unorm.data_ptr(), mask_u8.data_ptr(), br, bc, t, r, d,
+                      float(gammas[0]), float(gammas[1]), float(gammas[2]), sim.data_ptr(), _stream())
         return sim
 
-    def words_bwd(self, qhat, vhat, gram, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
+    def words_bwd(self, qhat, qhat16, vhat, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
                   row_offset, b_total, gammas):
         """Returns (dqhat (br,T,D), dvhat (bc,R,D) partial over this rank's rows, kq (br,T))."""
+        gram = col["gram"]
         br, t, d = qhat.shape
         bc, r, _ = vhat.shape
         dev = qhat.device

@@ -80,9 +80,10 @@ class DamsmWordsLoss(torch.autograd.Function):
         qhat, qhat16, qnorm, qunorm = engine.l2norm_fwd(words3, want_bf16=engine.precision == "bf16")
         vhat_l, vhat16_l, vnorm, _ = engine.l2norm_fwd(regions3, want_bf16=engine.precision == "bf16")
         vhat = _all_gather_rows(vhat_l, group)
+        vhat16 = _all_gather_rows(vhat16_l, group) if vhat16_l is not None else None
         cls_all = _all_gather_rows(cls_local, group) if cls_local is not None else None
-        colside = engine.words_prepare_columns(vhat)
-        sim = engine.words_fwd(qhat, vhat, colside, qunorm, mask_u8, gammas)
+        colside = engine.words_prepare_columns(vhat, vhat16)
+        sim = engine.words_fwd(qhat, qhat16, vhat, colside, qunorm, mask_u8, gammas)
         row_lse, col_max, col_sum = engine.ce_stats(sim, cls_local, cls_all, row_offset)
         col_lse = combine_column_lse(col_max, col_sum, group)
         out2 = engine.ce_losses(sim, row_lse, col_lse, labels, row_offset, b_total)
@@ -90,18 +91,19 @@ class DamsmWordsLoss(torch.autograd.Function):
             dist.all_reduce(out2, group=group)
         ctx.engine, ctx.group, ctx.gammas = engine, group, gammas
         ctx.row_offset, ctx.b_total = row_offset, b_total
-        ctx.save_for_backward(regions3, words3, mask_u8, labels, qhat, vhat, colside, qnorm, qunorm, vnorm,
+        ctx.colside, ctx.qhat16 = colside, qhat16
+        ctx.save_for_backward(regions3, words3, mask_u8, labels, qhat, vhat, qnorm, qunorm, vnorm,
                               sim, row_lse, col_lse)
         ctx.mark_non_differentiable(sim)
         return out2[0].clone(), out2[1].clone(), sim
 
     @staticmethod
     def backward(ctx, g0, g1, _gsim):
-        (regions3, words3, mask_u8, labels, qhat, vhat, colside, qnorm, qunorm, vnorm,
+        (regions3, words3, mask_u8, labels, qhat, vhat, qnorm, qunorm, vnorm,
          sim, row_lse, col_lse) = ctx.saved_tensors
-        eng = ctx.engine
+        eng, colside = ctx.engine, ctx.colside
         gscale = torch.stack([g0.reshape(()), g1.reshape(())]).to(torch.float32)
-        dqhat, dvhat, kq = eng.words_bwd(qhat, vhat, colside, qunorm, mask_u8, sim, row_lse, col_lse, labels,
+        dqhat, dvhat, kq = eng.words_bwd(qhat, ctx.qhat16, vhat, colside, qunorm, mask_u8, sim, row_lse, col_lse, labels,
                                          gscale, ctx.row_offset, ctx.b_total, ctx.gammas)
         dregions3 = dwords3 = None
         if ctx.needs_input_grad[0]:

@@ -1,0 +1,62 @@
+"""bf16 tensor-core (tcgen05) path against the fp64 oracle fed the same bf16-rounded inputs.
+Tolerance (BASELINE.json north_star): rel <= 2e-3 on losses and gradients."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import damsm_oracle as O
+
+pytestmark = pytest.mark.gpu
+pkg = importlib.import_module("t2i_clip-gan_b200")
+TOL = 2e-3
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def rounded(x):
+    xb = dict(x)
+    for k in ("words", "regions"):
+        xb[k] = torch.tensor(x[k]).bfloat16().float().numpy()
+    return xb
+
+
+@pytest.mark.parametrize("B,T,R,seed", [(6, 5, 9, 1), (12, 18, 49, 2), (9, 28, 49, 3), (5, 77, 49, 4), (4, 77, 196, 5),
+                                        (7, 40, 120, 6), (3, 64, 127, 7), (20, 18, 196, 8)])
+def test_tc_forward_scores(B, T, R, seed):
+    """sim matrix (before masking / CE) of the tcgen05 kernel vs the exact fp32 kernel and the oracle."""
+    x = rounded(O.make_inputs(B, T, R, seed=seed, class_ids=False))
+    ref = 10.0 * O.words_sim(x["words"], x["regions"], x["mask"], 4.0, 5.0)
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        eng = pkg.get_engine(prec)
+        w = torch.tensor(x["words"], device="cuda")
+        r = torch.tensor(x["regions"], device="cuda")
+        qhat, qhat16, _, qun = eng.l2norm_fwd(w, want_bf16=prec == "bf16")
+        vhat, vhat16, _, _ = eng.l2norm_fwd(r, want_bf16=prec == "bf16")
+        col = eng.words_prepare_columns(vhat, vhat16)
+        m = torch.tensor(x["mask"], device="cuda").to(torch.uint8)
+        outs[prec] = eng.words_fwd(qhat, qhat16, vhat, col, qun, m, (4.0, 5.0, 10.0)).cpu().numpy()
+    assert np.abs(outs["fp32"] - ref).max() <= 1e-4
+    err = np.abs(outs["bf16"] - ref).max() / np.abs(ref).max()
+    assert err <= TOL, err
+
+
+@pytest.mark.parametrize("B,T,R,cls,seed", [(8, 18, 49, True, 11), (6, 77, 196, False, 12), (16, 28, 49, True, 13)])
+def test_tc_words_loss_and_grads(B, T, R, cls, seed):
+    x = rounded(O.make_inputs(B, T, R, seed=seed, class_ids=cls, n_classes=4))
+    o = O.words_loss(x["words"], x["regions"], x["mask"], x["labels"], x["class_ids"], 4.0, 5.0, 10.0)
+    w = torch.tensor(x["words"], device="cuda").requires_grad_(True)
+    r = torch.tensor(x["regions"], device="cuda").requires_grad_(True)
+    l0, l1, _ = pkg.words_loss(r.permute(0, 2, 1), w.permute(0, 2, 1), torch.arange(B, device="cuda"), None,
+                               x["class_ids"], B, torch.tensor(x["mask"]), 4.0, 5.0, 10.0, precision="bf16")
+    (l0 + l1).backward()
+    assert abs(l0.item() - o["loss0"]) <= TOL * max(1, abs(o["loss0"]))
+    assert abs(l1.item() - o["loss1"]) <= TOL * max(1, abs(o["loss1"]))
+    assert rel(w.grad.cpu().numpy(), o["dwords"]) <= TOL
+    assert rel(r.grad.cpu().numpy(), o["dregions"]) <= TOL
