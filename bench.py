@@ -191,7 +191,7 @@ def main():
     args = ap.parse_args()
 
     pkg = importlib.import_module("t2i_clip-gan_b200")
-    has_tc = args.impl == "ours" and hasattr(pkg._lib.load(), "damsm_words_fwd_bf16")
+    has_tc = args.impl == "ours" and hasattr(pkg._lib.load(), "damsm_words_fwd_tc")
     if args.workload is None:
         args.workload = "c5" if has_tc else "c2"
     w = dict(WORKLOADS[args.workload])
@@ -337,7 +337,7 @@ def measure_roofline(pkg, w, dev, bl, B, rank, group, prec):
     peaks = load_peaks()
     with torch.no_grad():
         words3, regions3 = dev["words"].detach(), dev["regions"].detach()
-        qhat, qhat16, qnorm, qunorm = eng.l2norm_fwd(words3, want_bf16=prec == "bf16")
+        qhat, qhat16, qnorm, qunorm = eng.l2norm_fwd(words3, want_bf16=prec == "bf16", pad8=True)
         vhat_l, vhat16_l, vnorm, _ = eng.l2norm_fwd(regions3, want_bf16=prec == "bf16")
         vhat = pkg.ops._all_gather_rows(vhat_l, group)
         mask_u8 = (dev["mask"] != 0).to(torch.uint8).contiguous()

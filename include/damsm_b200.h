@@ -55,17 +55,18 @@ DAMSM_API int damsm_device_info(int *sm_count, int *cc_major, int *cc_minor, int
 /* ---- l2norm prologue / epilogue (losses.py:13-18, applied at :115-116; GlobalAttention.py:60-61) --------
  * x is viewed as (nb, nv, D) through element strides (sb, sv, sd), so the reference's permuted
  * (B,D,T)/(B,D,R) views, the CLS-sliced region view and 4-D (B,D,h,w) tensors are read in place.
- * xhat = x / (||x||_2 + 1e-8).  Outputs (each may be NULL): xhat_f32 (nb,nv,D), xhat_bf16 (nb,nv,D),
- * norm (nb,nv) = ||x||, unorm (nb,nv) = ||xhat|| (the norm CosineSimilarity sees at losses.py:197). */
+ * xhat = x / (||x||_2 + 1e-8).  Outputs (each may be NULL): xhat_f32 (nb,nv,D), xhat_f16 (nb,nv_pad,D),
+ * norm (nb,nv) = ||x||, unorm (nb,nv) = ||xhat|| (the norm CosineSimilarity sees at losses.py:197).
+ * xhat_f16 (fp16 operand copy for the tensor-core path) has rows [nv, nv_pad) zeroed (nv_pad < nv means nv). */
 DAMSM_API int damsm_l2norm_fwd(const void *x, int dtype, int64_t nb, int64_t nv, int64_t d,
                      int64_t sb, int64_t sv, int64_t sd,
-                     float *xhat_f32, void *xhat_bf16, float *norm, float *unorm, void *stream);
+                     float *xhat_f32, void *xhat_f16, int64_t nv_pad, float *norm, float *unorm, void *stream);
 /* dx = (dxhat' - (xhat.dxhat') x/||x||) / (||x||+1e-8) with dxhat' = dxhat - kq*xhat/unorm^2
  * (kq may be NULL; it carries the cosine's dependence on ||qhat||).  dx has x's dtype and is written
- * through element strides (dsb, dsv, dsd). */
+ * through element strides (dsb, dsv, dsd); dxhat vector (b,v) starts at dxhat + b*gsb + v*gsv (fp32, D contiguous). */
 DAMSM_API int damsm_l2norm_bwd(const void *x, int dtype, int64_t nb, int64_t nv, int64_t d,
                      int64_t sb, int64_t sv, int64_t sd,
-                     const float *norm, const float *dxhat, const float *kq,
+                     const float *norm, const float *dxhat, int64_t gsb, int64_t gsv, const float *kq,
                      void *dx, int64_t dsb, int64_t dsv, int64_t dsd, void *stream);
 
 /* ---- per-image Gram matrices G_j = vhat_j vhat_j^T (bc,R,R): ||c_t||^2 = a_t^T G a_t replaces the
@@ -94,18 +95,37 @@ DAMSM_API int damsm_words_bwd_f32(const float *qhat, const float *vhat, const fl
 /* host: dynamic shared memory the fused fp32 pair kernel needs for (T,R); <0 if unsupported */
 DAMSM_API int64_t damsm_words_f32_smem_bytes(int64_t t, int64_t r);
 
-/* ---- bf16 tensor-core path (tcgen05 / TMEM / TMA), same math as damsm_words_fwd_f32 ---------------------
- * qhat16 (br,T,D), vhat16 (bc,R,D): bf16 copies of the normalised embeddings (damsm_l2norm_fwd).
- * gx (bc, R+1, RK) bf16 with RK = damsm_words_tc_gx_cols(R): the Gram matrix of each image, columns
+/* ---- tensor-core path (tcgen05 / TMEM / TMA) for the bf16-input configurations; same math as
+ * damsm_words_fwd_f32.  All MMA operands are bounded (|qhat|,|vhat|,|G| <= 1, e2 in [1, e^gamma1]), so they are
+ * staged as fp16 -- same kind::f16 tensor rate as bf16 with 3 more mantissa bits -- and accumulated in fp32.
+ * qhat16 (br,q_rows,D), vhat16 (bc,R,D): fp16 copies of the normalised embeddings (damsm_l2norm_fwd).
+ * gx (bc, R+1, RK) fp16 with RK = damsm_words_tc_gx_cols(R): the Gram matrix of each image, columns
  * zero-padded to a multiple of 64, plus one appended row of ones (it makes the second GEMM deliver the
  * softmax-over-regions denominators).  Parity target: rel <= 2e-3 against the fp32 reference. */
 DAMSM_API int64_t damsm_words_tc_gx_cols(int64_t r);
-DAMSM_API int damsm_gram_pack_bf16(const float *gram, int64_t bc, int64_t r, void *gx, void *stream);
+DAMSM_API int damsm_gram_pack_tc(const float *gram, int64_t bc, int64_t r, void *gx, void *stream);
 /* host: dynamic shared memory of the tcgen05 kernel for (T,R,D); <0 if the shape is unsupported */
 DAMSM_API int64_t damsm_words_tc_smem_bytes(int64_t t, int64_t r, int64_t d);
-DAMSM_API int damsm_words_fwd_bf16(const void *qhat16, const void *vhat16, const void *gx, const float *unorm,
-                                   const uint8_t *mask, int64_t br, int64_t bc, int64_t t, int64_t r, int64_t d,
-                                   float gamma1, float gamma2, float gamma3, float *sim, void *stream);
+/* q_rows = rows per caption in qhat16 (T, or T padded to a multiple of 8 with zero rows) */
+DAMSM_API int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
+                                   const float *unorm, const uint8_t *mask, int64_t br, int64_t bc, int64_t t,
+                                   int64_t r, int64_t d, float gamma1, float gamma2, float gamma3, float *sim,
+                                   void *stream);
+/* Backward of the tensor-core path.  A fused tcgen05 kernel recomputes S, P, A, M per pair on chip and emits
+ * dS, A and diag(b)A as (scaled) fp16 into `workspace`, one chunk of caption rows at a time
+ * (damsm_words_bwd_tc_row_bytes() bytes per caption row; at least one row must fit); three plain GEMMs per
+ * chunk (cuBLAS, fp16 in / fp32 accumulate) then contract them with qhat / vhat / each other:
+ *   dvhat (bc,R,D) += dS^T qhat   [ACCUMULATED, caller zeroes]     dqhat (br,q_rows,D) = dS vhat   [OVERWRITTEN]
+ *   hmat (bc,R,R) += A^T diag(b) A [ACCUMULATED]                   kq (br,T)                       [ACCUMULATED]
+ * qhat16 must be padded: q_rows == T rounded up to a multiple of 8. */
+DAMSM_API int64_t damsm_words_bwd_tc_row_bytes(int64_t bc, int64_t t, int64_t r);
+DAMSM_API int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
+                                   const float *unorm, const uint8_t *mask, const float *sim, const float *row_lse,
+                                   const float *col_lse, const int64_t *labels, const float *gscale,
+                                   int64_t row_offset, int64_t b_total, int64_t br, int64_t bc, int64_t t, int64_t r,
+                                   int64_t d, float gamma1, float gamma2, float gamma3, void *workspace,
+                                   int64_t workspace_bytes, float *dqhat, float *dvhat, float *hmat, float *kq,
+                                   void *stream);
 
 /* ---- class_ids masking + both CrossEntropyLoss() (losses.py:55-66,84-88 / :224-232,256-269) -----------
  * logits (br,bc) row block of the (b_total x b_total) matrix.  In place: logits[i][j] = -inf where

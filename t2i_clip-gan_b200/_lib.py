@@ -20,8 +20,8 @@ SIGNATURES = {
     "damsm_version": [],
     "damsm_last_error": [],
     "damsm_device_info": [_p, _p, _p, _p],
-    "damsm_l2norm_fwd": [_p, _i, _l, _l, _l, _l, _l, _l, _p, _p, _p, _p, _p],
-    "damsm_l2norm_bwd": [_p, _i, _l, _l, _l, _l, _l, _l, _p, _p, _p, _p, _l, _l, _l, _p],
+    "damsm_l2norm_fwd": [_p, _i, _l, _l, _l, _l, _l, _l, _p, _p, _l, _p, _p, _p],
+    "damsm_l2norm_bwd": [_p, _i, _l, _l, _l, _l, _l, _l, _p, _p, _l, _l, _p, _p, _l, _l, _l, _p],
     "damsm_gram_f32": [_p, _l, _l, _l, _p, _p],
     "damsm_gram_bwd_f32": [_p, _p, _l, _l, _l, _p, _p],
     "damsm_words_fwd_f32": [_p, _p, _p, _p, _p, _l, _l, _l, _l, _l, _f, _f, _f, _p, _p],
@@ -29,9 +29,12 @@ SIGNATURES = {
                             _p, _p, _p, _p, _p],
     "damsm_words_f32_smem_bytes": [_l, _l],
     "damsm_words_tc_gx_cols": [_l],
-    "damsm_gram_pack_bf16": [_p, _l, _l, _p, _p],
+    "damsm_gram_pack_tc": [_p, _l, _l, _p, _p],
     "damsm_words_tc_smem_bytes": [_l, _l, _l],
-    "damsm_words_fwd_bf16": [_p, _p, _p, _p, _p, _l, _l, _l, _l, _l, _f, _f, _f, _p, _p],
+    "damsm_words_fwd_tc": [_p, _l, _p, _p, _p, _p, _l, _l, _l, _l, _l, _f, _f, _f, _p, _p],
+    "damsm_words_bwd_tc_row_bytes": [_l, _l, _l],
+    "damsm_words_bwd_tc": [_p, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _l, _l, _l, _f, _f, _f,
+                             _p, _l, _p, _p, _p, _p, _p],
     "damsm_ce_stats_f32": [_p, _p, _p, _l, _l, _l, _p, _p, _p, _p],
     "damsm_ce_losses_f32": [_p, _p, _p, _p, _l, _l, _l, _l, _p, _p],
     "damsm_cos_logits_f32": [_p, _l, _p, _l, _l, _l, _l, _f, _f, _p, _p, _p, _p],
@@ -41,13 +44,14 @@ SIGNATURES = {
     "damsm_func_attention_bwd_f32": [_p, _p, _p, _l, _l, _l, _p, _p, _p, _p, _l, _l, _l, _l, _f, _p, _p, _p, _p],
 }
 _RESTYPE = {"damsm_last_error": C.c_char_p, "damsm_words_f32_smem_bytes": C.c_int64,
-            "damsm_words_tc_gx_cols": C.c_int64, "damsm_words_tc_smem_bytes": C.c_int64}
+            "damsm_words_tc_gx_cols": C.c_int64, "damsm_words_tc_smem_bytes": C.c_int64,
+            "damsm_words_bwd_tc_row_bytes": C.c_int64}
 
 # kernels launched per successful call of each entry point (bench.py reports the total as gpu_launches)
 LAUNCHES = {
     "damsm_l2norm_fwd": 1, "damsm_l2norm_bwd": 1, "damsm_gram_f32": 1, "damsm_gram_bwd_f32": 1,
     "damsm_words_fwd_f32": 1, "damsm_words_bwd_f32": 1,
-    "damsm_gram_pack_bf16": 1, "damsm_words_fwd_bf16": 1, "damsm_ce_stats_f32": 2, "damsm_ce_losses_f32": 1,
+    "damsm_gram_pack_tc": 1, "damsm_words_fwd_tc": 1, "damsm_words_bwd_tc": 1, "damsm_ce_stats_f32": 2, "damsm_ce_losses_f32": 1,
     "damsm_cos_logits_f32": 4, "damsm_cos_logits_bwd_f32": 5,
     "damsm_func_attention_fwd_f32": 1, "damsm_func_attention_bwd_f32": 1,
 }

@@ -105,7 +105,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 }
 
 // ---------------------------------------------------------------------------------------------- UMMA
-// Shared-memory matrix descriptor, K-major operand stored as rows of 128 B (64 bf16) with the 128-byte
+// Shared-memory matrix descriptor, K-major operand stored as rows of 128 B (64 halves) with the 128-byte
 // swizzle (what TMA SWIZZLE_128B produces): 8-row groups are 1024 B apart (SBO), tile base 1024-B aligned.
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -116,13 +116,14 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                            // layout type: SWIZZLE_128B
   return d;
 }
-// Instruction descriptor for kind::f16 with bf16 A/B (both K-major), fp32 accumulate, M=128, N=n.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
-  return (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | ((uint32_t)(n >> 3) << 17) |
+// Instruction descriptor for kind::f16 with fp16 A/B (both K-major; format code 0 = F16, 1 would be BF16),
+// fp32 accumulate, M=128, N=n.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
+  return (1u << 4) /*D=f32*/ | (0u << 7) /*A=f16*/ | (0u << 10) /*B=f16*/ | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(128 >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -136,7 +137,7 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Byte offset of element (row, col) of a K-major [rows x 64] bf16 tile stored with the 128-byte swizzle.
+// Byte offset of element (row, col) of a K-major [rows x 64] 16-bit tile stored with the 128-byte swizzle.
 __device__ __forceinline__ uint32_t sw128_offset(int row, int col) {
   return (uint32_t)(row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1)));
 }

@@ -38,20 +38,24 @@ class CudaEngine:
         _lib.load()
 
     # ---- l2norm ---------------------------------------------------------------------------------------
-    def l2norm_fwd(self, x3: torch.Tensor, want_bf16: bool = False):
-        """x3: (nb, nv, D) strided view.  Returns (xhat_f32, xhat_bf16|None, norm, unorm)."""
+    def l2norm_fwd(self, x3: torch.Tensor, want_bf16: bool = False, pad8: bool = False):
+        """x3: (nb, nv, D) strided view.  Returns (xhat_f32, xhat_16|None, norm, unorm).  ``want_bf16`` asks for
+        the 16-bit operand copy of the tensor-core path (stored as fp16: |xhat| <= 1, so fp16 keeps 3 more
+        mantissa bits than bf16 at the same tensor-core rate); with ``pad8`` its vector count is padded to a
+        multiple of 8 with zero rows."""
         _require_cuda(x3)
         if x3.dtype not in _DTYPE_CODE:
             raise TypeError(f"unsupported dtype {x3.dtype}")
         nb, nv, d = x3.shape
         dev = x3.device
         xhat = torch.empty((nb, nv, d), device=dev, dtype=torch.float32)
-        xhat16 = torch.empty((nb, nv, d), device=dev, dtype=torch.bfloat16) if want_bf16 else None
+        nv_pad = (nv + 7) // 8 * 8 if pad8 else nv
+        xhat16 = torch.empty((nb, nv_pad, d), device=dev, dtype=torch.float16) if want_bf16 else None
         norm = torch.empty((nb, nv), device=dev, dtype=torch.float32)
         unorm = torch.empty((nb, nv), device=dev, dtype=torch.float32)
         sb, sv, sd = x3.stride()
         _lib.call("damsm_l2norm_fwd", x3.data_ptr(), _DTYPE_CODE[x3.dtype], nb, nv, d, sb, sv, sd,
-                  xhat.data_ptr(), _lib.ptr(xhat16), norm.data_ptr(), unorm.data_ptr(), _stream())
+                  xhat.data_ptr(), _lib.ptr(xhat16), nv_pad, norm.data_ptr(), unorm.data_ptr(), _stream())
         return xhat, xhat16, norm, unorm
 
     def l2norm_bwd(self, x3: torch.Tensor, norm, dxhat, kq=None):
@@ -62,9 +66,11 @@ class CudaEngine:
         dx = torch.empty_strided(x3.shape, _dense_strides_like(x3), device=x3.device, dtype=x3.dtype)
         sb, sv, sd = x3.stride()
         dsb, dsv, dsd = dx.stride()
-        dxhat = dxhat.contiguous()
+        if dxhat.stride(2) != 1:
+            dxhat = dxhat.contiguous()
         _lib.call("damsm_l2norm_bwd", x3.data_ptr(), _DTYPE_CODE[x3.dtype], nb, nv, d, sb, sv, sd,
-                  norm.data_ptr(), dxhat.data_ptr(), _lib.ptr(kq), dx.data_ptr(), dsb, dsv, dsd, _stream())
+                  norm.data_ptr(), dxhat.data_ptr(), dxhat.stride(0), dxhat.stride(1), _lib.ptr(kq),
+                  dx.data_ptr(), dsb, dsv, dsd, _stream())
         return dx
 
     # ---- word / region scores ---------------------------------------------------------------------------
@@ -77,8 +83,8 @@ class CudaEngine:
         col = {"gram": gram}
         if self.precision == "bf16":
             rk = _lib.load().damsm_words_tc_gx_cols(r)
-            gx = torch.empty((bc, r + 1, rk), device=vhat.device, dtype=torch.bfloat16)
-            _lib.call("damsm_gram_pack_bf16", gram.data_ptr(), bc, r, gx.data_ptr(), _stream())
+            gx = torch.empty((bc, r + 1, rk), device=vhat.device, dtype=torch.float16)
+            _lib.call("damsm_gram_pack_tc", gram.data_ptr(), bc, r, gx.data_ptr(), _stream())
             col["gx"] = gx
             col["vhat16"] = vhat16
         return col
@@ -89,7 +95,8 @@ class CudaEngine:
         bc, r, _ = vhat.shape
         sim = torch.empty((br, bc), device=qhat.device, dtype=torch.float32)
         if self.precision == "bf16":
-            _lib.call("damsm_words_fwd_bf16", qhat16.data_ptr(), col["vhat16"].data_ptr(), col["gx"].data_ptr(),
+            _lib.call("damsm_words_fwd_tc", qhat16.data_ptr(), qhat16.shape[1], col["vhat16"].data_ptr(),
+                      col["gx"].data_ptr(),
                       unorm.data_ptr(), mask_u8.data_ptr(), br, bc, t, r, d,
                       float(gammas[0]), float(gammas[1]), float(gammas[2]), sim.data_ptr(), _stream())
         else:
@@ -105,6 +112,9 @@ class CudaEngine:
         br, t, d = qhat.shape
         bc, r, _ = vhat.shape
         dev = qhat.device
+        if self.precision == "bf16":
+            return self._words_bwd_tc(qhat16, vhat, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
+                                      row_offset, b_total, gammas, br, bc, t, r, d)
         dqhat = torch.zeros((br, t, d), device=dev, dtype=torch.float32)
         dvhat = torch.zeros((bc, r, d), device=dev, dtype=torch.float32)
         hmat = torch.zeros((bc, r, r), device=dev, dtype=torch.float32)
@@ -116,6 +126,29 @@ class CudaEngine:
                   dqhat.data_ptr(), dvhat.data_ptr(), hmat.data_ptr(), kq.data_ptr(), _stream())
         _lib.call("damsm_gram_bwd_f32", hmat.data_ptr(), vhat.data_ptr(), bc, r, d, dvhat.data_ptr(), _stream())
         return dqhat, dvhat, kq
+
+    # scratch for the tensor-core backward (bytes); the fused kernel + GEMMs run chunk by chunk inside it
+    tc_workspace_bytes = 6 << 30
+
+    def _words_bwd_tc(self, qhat16, vhat, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
+                      row_offset, b_total, gammas, br, bc, t, r, d):
+        dev = vhat.device
+        tp = qhat16.shape[1]
+        lib = _lib.load()
+        row_bytes = lib.damsm_words_bwd_tc_row_bytes(bc, t, r)
+        ws_bytes = min(max(row_bytes, self.tc_workspace_bytes // row_bytes * row_bytes), row_bytes * br)
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        dqhat = torch.empty((br, tp, d), device=dev, dtype=torch.float32)
+        dvhat = torch.zeros((bc, r, d), device=dev, dtype=torch.float32)
+        hmat = torch.zeros((bc, r, r), device=dev, dtype=torch.float32)
+        kq = torch.zeros((br, t), device=dev, dtype=torch.float32)
+        _lib.call("damsm_words_bwd_tc", qhat16.data_ptr(), tp, col["vhat16"].data_ptr(), col["gx"].data_ptr(),
+                  unorm.data_ptr(), mask_u8.data_ptr(), sim.data_ptr(), row_lse.data_ptr(), col_lse.data_ptr(),
+                  _lib.ptr(labels), gscale.data_ptr(), int(row_offset), int(b_total), br, bc, t, r, d,
+                  float(gammas[0]), float(gammas[1]), float(gammas[2]), ws.data_ptr(), ws_bytes,
+                  dqhat.data_ptr(), dvhat.data_ptr(), hmat.data_ptr(), kq.data_ptr(), _stream())
+        _lib.call("damsm_gram_bwd_f32", hmat.data_ptr(), vhat.data_ptr(), bc, r, d, dvhat.data_ptr(), _stream())
+        return dqhat[:, :t, :], dvhat, kq
 
     # ---- masked bidirectional cross-entropy ---------------------------------------------------------------
     def ce_stats(self, logits, cls_rows, cls_cols, row_offset):

@@ -77,7 +77,7 @@ class DamsmWordsLoss(torch.autograd.Function):
         if regions3.shape[0] != bl:
             raise ValueError("words and regions must have the same (local) batch size")
         b_total, row_offset = bl * world, rank * bl
-        qhat, qhat16, qnorm, qunorm = engine.l2norm_fwd(words3, want_bf16=engine.precision == "bf16")
+        qhat, qhat16, qnorm, qunorm = engine.l2norm_fwd(words3, want_bf16=engine.precision == "bf16", pad8=True)
         vhat_l, vhat16_l, vnorm, _ = engine.l2norm_fwd(regions3, want_bf16=engine.precision == "bf16")
         vhat = _all_gather_rows(vhat_l, group)
         vhat16 = _all_gather_rows(vhat16_l, group) if vhat16_l is not None else None

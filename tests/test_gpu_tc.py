@@ -37,7 +37,7 @@ def test_tc_forward_scores(B, T, R, seed):
         eng = pkg.get_engine(prec)
         w = torch.tensor(x["words"], device="cuda")
         r = torch.tensor(x["regions"], device="cuda")
-        qhat, qhat16, _, qun = eng.l2norm_fwd(w, want_bf16=prec == "bf16")
+        qhat, qhat16, _, qun = eng.l2norm_fwd(w, want_bf16=prec == "bf16", pad8=True)
         vhat, vhat16, _, _ = eng.l2norm_fwd(r, want_bf16=prec == "bf16")
         col = eng.words_prepare_columns(vhat, vhat16)
         m = torch.tensor(x["mask"], device="cuda").to(torch.uint8)
