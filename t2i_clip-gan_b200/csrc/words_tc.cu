@@ -1,34 +1,42 @@
-// Tensor-core path (bf16-input configurations) of the word/region matching scores: tcgen05.mma with TMEM accumulators, operands
-// staged by TMA, both softmaxes / cosine / log-sum-exp in registers.  One CTA owns one caption and streams
-// images; per (caption i, image j) pair (losses.py:95-216 for every pair, :228-254):
+// Tensor-core path (bf16-input configurations) of the word/region matching loss: tcgen05.mma with TMEM
+// accumulators, operands staged by TMA, both softmaxes / cosine / log-sum-exp in registers.  One CTA owns one
+// caption and streams images; per (caption i, image j) pair (losses.py:95-216 for every pair, :228-254):
 //
 //   GEMM1  S^T[r][t]  = sum_d vhat_j[r][d] qhat_i[t][d]          M = regions (1-2 tiles of 128), N = words, K = D
-//   regs   e1 = mask_t exp(S);  P = e1 / sum_t e1  (in-thread: a thread owns one region row)
+//   regs   e1 = mask_t exp(S);  P = e1 / sum_t e1                (a thread owns one region row and half the words)
 //          e2 = exp(gamma1 P)  -> fp16 -> shared memory as the K-major B operand of GEMM2
-//   GEMM2  M'^T[r][t] = sum_r' Gx_j[r][r'] e2[r'][t]              K = regions; Gx = [G ; 1^T] so that the extra row
+//   GEMM2  M'^T[r][t] = sum_r' Gx_j[r][r'] e2[r'][t]              K = regions; Gx = [G ; 1^T]: the appended row of ones
 //                                                                yields Y_t = sum_r e2 (softmax-over-regions denominator)
-//   regs   N'_t = sum_r e2 S, NN_t = sum_r e2 M'  (warp butterfly + smem across warps)
+//   regs   N'_t = sum_r e2 S, NN_t = sum_r e2 M'  (warp butterfly + shared memory across warps)
 //          rho_t = (N'/Y) / (max(sqrt(NN)/Y, eps) max(u_t, eps)),  sim = gamma3/gamma2 log sum_t exp(gamma2 rho_t)
+//   bwd    the same recompute, then dS = a A + P (dP - W), dP = gamma1 A (a S - b M), W = sum_t P dP; dS, A and
+//          diag(b) A leave the chip as scaled fp16 tiles that three plain GEMMs (cuBLAS) contract per chunk.
 //
-// Regions live on the MMA M axis (TMEM lanes) because then the softmax over words, its backward column term
-// and every per-region quantity are in-thread, and the accumulators (2 x NT columns each) leave TMEM room.
-// Orientation, budgets and the roofline are discussed in DESIGN.md.
+// Regions live on the MMA M axis (TMEM lanes): the softmax over words, its backward column term and every
+// per-region quantity are then thread-local, and the accumulators (NT columns per tile) leave TMEM room for a
+// second S buffer, so GEMM1 of the next image overlaps the register work of the current one.
+// Warp roles: 0-15 softmax/epilogue (TMEM lane quadrant = warp%4, tile = (warp/4)%2, word half = warp/8),
+// 16 TMA producer, 17 MMA issuer.  Budgets and the roofline are in DESIGN.md.
 #include <cublas_v2.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace damsm {
 using namespace tc;
 
-constexpr int TC_THREADS = 320;     // warps 0-7: softmax/epilogue (one per TMEM lane quadrant x 2 tiles), 8: TMA, 9: MMA
+constexpr int TC_THREADS = 576;
 constexpr int TC_STAGES = 3;
+constexpr float kLog2e = 1.4426950408889634f;
 
 struct TcLayout {
-  int rs;            // rows per operand stage (ceil8(R+1))
+  int rs;            // operand rows fetched per stage (ceil8(R+1))
   int tiles;         // M tiles of 128 region rows
   int k2_steps;      // K=16 steps of GEMM2 (ceil16(R)/16)
   int nkb_d, nkb_r;  // 64-wide k-blocks of GEMM1 / GEMM2
+  int nbuf;          // S accumulators in TMEM (2 when 3*tiles*NT <= 512 columns)
+  int act_warps;     // softmax warps that own at least one row below max(16*k2_steps, R+1)
   uint32_t q_bytes, stage_bytes, e2_bytes, misc_off, total;
 };
 
@@ -39,18 +47,20 @@ __host__ __device__ inline TcLayout tc_layout(int NT, int R, int D) {
   l.k2_steps = (R + 15) / 16;
   l.nkb_d = D / 64;
   l.nkb_r = (l.k2_steps * 16 + 63) / 64;
+  l.nbuf = (3 * l.tiles * NT <= 512) ? 2 : 1;
+  const int act_rows = (l.k2_steps * 16 > R + 1) ? l.k2_steps * 16 : R + 1;
+  l.act_warps = 2 * ((act_rows + 31) / 32);
   l.q_bytes = (uint32_t)l.nkb_d * NT * 128;
-  l.stage_bytes = ((uint32_t)l.rs * 128 + 1023) & ~1023u;
   l.e2_bytes = (uint32_t)l.nkb_r * NT * 128;
+  l.stage_bytes = ((uint32_t)l.rs * 128 + 1023) & ~1023u;
+  // An M=128 MMA reads 128 operand rows per tile; rows past `rs` of the last tile come from whatever follows the
+  // stage.  Their TMEM lanes are never used, but the bytes must be finite fp16 (zero-initialised / operand data):
+  // the overrun of the last stage may reach into the e2 buffer but not into the fp32 bookkeeping behind it.
+  if ((uint32_t)l.tiles * 16384 > l.stage_bytes + l.e2_bytes) l.stage_bytes = (uint32_t)l.tiles * 16384;
   l.misc_off = l.q_bytes + TC_STAGES * l.stage_bytes + l.e2_bytes;
-  // misc: barriers (16 x 8 B) + tmem ptr + mask words + misc scalars, then per-word vectors
-  // u, Y, xs, rho, n, iy [NT] + coefficient float4 [NT] + red1/red2 [8][NT]
-  l.total = l.misc_off + 256 + 4 * (6 * NT + 4 * NT + 16 * NT);
-  // an M=128 MMA always reads 128 operand rows: the rows past `rs` of the last tile come from whatever
-  // follows the stage (their TMEM lanes are ignored) but must stay inside the allocation
-  const uint32_t reach = l.q_bytes + (TC_STAGES - 1) * l.stage_bytes + (uint32_t)l.tiles * 16384;
-  if (l.total < reach) l.total = reach;
-  l.total += 1024; /* alignment slack */
+  // misc: 256 B of barriers / scalars, then floats: u,Y,xs,rho,n,iy,tb,tb2 [NT] + vc float4 [NT] +
+  // red1/red2 [16][NT/2] + zbuf/wbuf [2][256]
+  l.total = l.misc_off + 256 + 4 * (8 * NT + 4 * NT + 16 * NT + 1024) + 1024 /*alignment slack*/;
   return l;
 }
 
@@ -73,213 +83,328 @@ struct TcParams {
   float scale_ds, scale_ba;           // power-of-two scales that keep dS and diag(b)A in fp16's normal range
 };
 
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2 *>(&v));
+}
+
+// TMEM -> registers, N consecutive fp32 columns of this thread's lane
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float *v) {
+  static_assert(N == 8 || N == 16 || N == 32, "tmem_ld width");
+  if constexpr (N == 32) {
+    tmem_ld16(taddr, v);
+    tmem_ld16(taddr + 16, v + 16);
+  } else if constexpr (N == 16) {
+    tmem_ld16(taddr, v);
+  } else {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+  }
+}
+
+// Column sums over the 32 lanes of a warp of N per-thread values; lane L returns the sum of column L % N.
+template <int N>
+__device__ __forceinline__ float warp_colsum(float (&v)[N], int lane) {
+#pragma unroll
+  for (int s = 16; s >= N; s >>= 1) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], s);
+  }
+#pragma unroll
+  for (int s = (N < 32 ? N / 2 : 16); s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int k = 0; k < s; ++k) {
+      const float send = upper ? v[k] : v[k + s];
+      const float keep = upper ? v[k + s] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
 template <int NT, bool BWD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
-                    const __grid_constant__ CUtensorMap tmG, TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+                const __grid_constant__ CUtensorMap tmG, TcParams p) {
+  constexpr int NH = NT / 2;                 // words per softmax thread
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const TcLayout L = tc_layout(NT, p.R, p.D);
   uint8_t *Qs = smem;
   uint8_t *stages = Qs + L.q_bytes;
   uint8_t *E2 = stages + TC_STAGES * L.stage_bytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.misc_off);
+  uint8_t *misc = smem + L.misc_off;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(misc);
   uint64_t *full = bars, *empty = bars + TC_STAGES;
-  uint64_t *q_full = bars + 2 * TC_STAGES, *s_full = q_full + 1, *e2_ready = q_full + 2, *m_full = q_full + 3,
-           *s_free = q_full + 4, *m_free = q_full + 5;
+  uint64_t *q_full = bars + 2 * TC_STAGES;            // 6
+  uint64_t *s_full = q_full + 1;                      // 7,8   (one per S buffer)
+  uint64_t *s_free = q_full + 3;                      // 9,10
+  uint64_t *e2_ready = q_full + 5, *m_full = q_full + 6, *m_free = q_full + 7;   // 11,12,13
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 16);
-  uint32_t *maskw = tmem_ptr + 4;                       // 4 words: bit t = word t is a real word
-  float *vmisc = reinterpret_cast<float *>(maskw + 4);  // [0] = lse, [1] = g_ij
-  float *vu = reinterpret_cast<float *>(smem + L.misc_off + 256);   // [NT]
-  float *vY = vu + NT, *vxs = vY + NT, *vrho = vxs + NT, *vn = vrho + NT, *viy = vn + NT;   // [NT] each
-  float4 *vc = reinterpret_cast<float4 *>(viy + NT);    // [NT] backward coefficients
-  float *red1 = reinterpret_cast<float *>(vc + NT), *red2 = red1 + 8 * NT;   // [8][NT] each
+  float *vmisc = reinterpret_cast<float *>(tmem_ptr + 4);    // [0] = lse, [1] = g_ij
+  float *vu = reinterpret_cast<float *>(misc + 256);          // [NT] ||qhat_t||
+  float *vY = vu + NT, *vxs = vY + NT, *vrho = vxs + NT, *vn = vrho + NT, *viy = vn + NT;
+  float *tb = viy + NT;                                       // 0 for real words, -inf for padding and t >= T
+  float *tb2 = tb + NT;                                       // 0 for t < T, -inf for t >= T
+  float4 *vc = reinterpret_cast<float4 *>(tb2 + NT);          // [NT] backward coefficients
+  float *red1 = reinterpret_cast<float *>(vc + NT), *red2 = red1 + 16 * NH;   // [16][NH] each
+  float *zbuf = red2 + 16 * NH, *wbuf = zbuf + 512;           // [2][256] each
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = (BWD ? p.i0 : 0) + blockIdx.x;
   const int j0 = blockIdx.y * p.img_per_cta;
   const int j1 = min(p.bc, j0 + p.img_per_cta);
   const int T = p.T, R = p.R;
-  const int nsoft = L.tiles * 128;
+  const int nsoft = L.act_warps * 32;
+  const int nbuf = L.nbuf;
 
+  // operand rows past `rs` are read by the MMAs (ignored lanes): make every byte a finite fp16
+  for (uint32_t o = threadIdx.x * 16; o < L.misc_off; o += TC_THREADS * 16)
+    *reinterpret_cast<uint4 *>(smem + o) = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(m_full, 1);
-    mbar_init(e2_ready, nsoft); mbar_init(s_free, nsoft); mbar_init(m_free, nsoft);
+    mbar_init(q_full, 1); mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(m_full, 1);
+    mbar_init(&s_free[0], nsoft); mbar_init(&s_free[1], nsoft);
+    mbar_init(e2_ready, nsoft); mbar_init(m_free, nsoft);
     fence_barrier_init();
   }
-  if (threadIdx.x < 4) {
-    uint32_t w = 0;
-    for (int b = 0; b < 32; ++b) {
-      const int t = threadIdx.x * 32 + b;
-      if (t < T && p.mask[(int64_t)i * T + t]) w |= 1u << b;
-    }
-    maskw[threadIdx.x] = w;
-  }
   for (int t = threadIdx.x; t < NT; t += TC_THREADS) {
-    vu[t] = (t < T) ? p.unorm[(int64_t)i * T + t] : 1.f;
+    const bool in = t < T;
+    vu[t] = in ? p.unorm[(int64_t)i * T + t] : 1.f;
+    tb[t] = (in && p.mask[(int64_t)i * T + t]) ? 0.f : -INFINITY;
+    tb2[t] = in ? 0.f : -INFINITY;
     vc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     viy[t] = 0.f;
   }
-  if (warp == 9) tmem_alloc<512>(tmem_ptr);
-  if (warp == 8 && lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmV); prefetch_tmap(&tmG); }
+  if (warp == 17) tmem_alloc<512>(tmem_ptr);
+  if (warp == 16 && lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmV); prefetch_tmap(&tmG); }
+  fence_proxy_async_smem();           // the zero fill must be ordered before the TMA / MMA (async proxy) accesses
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t idesc = umma_idesc_f16(NT);
+  const uint32_t col_m = (uint32_t)(nbuf * L.tiles * NT);     // TMEM column of M'
 
-  if (warp == 8) {
+  if (warp == 16) {
     // ===================================== TMA producer =====================================
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, L.q_bytes);
       for (int kb = 0; kb < L.nkb_d; ++kb) tma_load_3d(Qs + kb * NT * 128, &tmQ, q_full, kb * 64, 0, i);
       int stage = 0, phase = 0;
-      for (int j = j0; j < j1; ++j) {
-        for (int kb = 0; kb < L.nkb_d + L.nkb_r; ++kb) {
+      auto load = [&](const CUtensorMap *m, int nkb, int j) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], (uint32_t)L.rs * 128);
-          if (kb < L.nkb_d) tma_load_3d(stages + stage * L.stage_bytes, &tmV, &full[stage], kb * 64, 0, j);
-          else              tma_load_3d(stages + stage * L.stage_bytes, &tmG, &full[stage], (kb - L.nkb_d) * 64, 0, j);
+          tma_load_3d(stages + stage * L.stage_bytes, m, &full[stage], kb * 64, 0, j);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
+      };
+      // same order as the MMA issuer consumes: with two S buffers GEMM1 of the next image precedes GEMM2
+      if (nbuf == 2) {
+        if (j0 < j1) load(&tmV, L.nkb_d, j0);
+        for (int j = j0; j < j1; ++j) {
+          if (j + 1 < j1) load(&tmV, L.nkb_d, j + 1);
+          load(&tmG, L.nkb_r, j);
+        }
+      } else {
+        for (int j = j0; j < j1; ++j) { load(&tmV, L.nkb_d, j); load(&tmG, L.nkb_r, j); }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 17) {
     // ===================================== MMA issuer =====================================
     if (elect_one()) {
       mbar_wait(q_full, 0);
       int stage = 0, phase = 0;
-      for (int j = j0, it = 0; j < j1; ++j, ++it) {
-        if (it > 0) mbar_wait(s_free, (it - 1) & 1);
+      auto gemm1 = [&](int it) {                       // S^T[buf] = vhat_j qhat_i^T
+        const int b = it % nbuf, use = it / nbuf;
+        if (use > 0) mbar_wait(&s_free[b], (use - 1) & 1);
         tc_fence_after();
-        for (int kb = 0; kb < L.nkb_d; ++kb) {           // GEMM1: S^T = vhat_j qhat_i^T
+        const uint32_t d0 = tmem_base + (uint32_t)(b * L.tiles * NT);
+        for (int kb = 0; kb < L.nkb_d; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a0 = smem_u32(stages + stage * L.stage_bytes), b0 = smem_u32(Qs + kb * NT * 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             for (int tl = 0; tl < L.tiles; ++tl)
-              umma_f16(tmem_base + tl * NT, umma_desc_k_sw128(a0 + tl * 16384 + k * 32),
-                        umma_desc_k_sw128(b0 + k * 32), idesc, (kb | k) != 0);
+              umma_f16(d0 + tl * NT, umma_desc_k_sw128(a0 + tl * 16384 + k * 32), umma_desc_k_sw128(b0 + k * 32),
+                       idesc, (kb | k) != 0);
           umma_commit(&empty[stage]);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(s_full);
+        umma_commit(&s_full[b]);
+      };
+      auto gemm2 = [&](int it) {                       // M'^T = Gx_j e2
         mbar_wait(e2_ready, it & 1);
         if (it > 0) mbar_wait(m_free, (it - 1) & 1);
         tc_fence_after();
         int left = L.k2_steps;
-        for (int kb = 0; kb < L.nkb_r; ++kb) {           // GEMM2: M'^T = Gx_j e2
+        for (int kb = 0; kb < L.nkb_r; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a0 = smem_u32(stages + stage * L.stage_bytes), b0 = smem_u32(E2 + kb * NT * 128);
           const int nk = min(4, left);
           for (int k = 0; k < nk; ++k)
             for (int tl = 0; tl < L.tiles; ++tl)
-              umma_f16(tmem_base + (L.tiles + tl) * NT, umma_desc_k_sw128(a0 + tl * 16384 + k * 32),
-                        umma_desc_k_sw128(b0 + k * 32), idesc, (kb | k) != 0);
+              umma_f16(tmem_base + col_m + tl * NT, umma_desc_k_sw128(a0 + tl * 16384 + k * 32),
+                       umma_desc_k_sw128(b0 + k * 32), idesc, (kb | k) != 0);
           left -= nk;
           umma_commit(&empty[stage]);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(m_full);
+      };
+      const int n = j1 - j0;
+      if (nbuf == 2) {
+        if (n > 0) gemm1(0);
+        for (int it = 0; it < n; ++it) {
+          if (it + 1 < n) gemm1(it + 1);
+          gemm2(it);
+        }
+      } else {
+        for (int it = 0; it < n; ++it) { gemm1(it); gemm2(it); }
       }
     }
-  } else if ((warp >> 2) < L.tiles) {
+  } else if (warp < 16 && (warp & 7) < L.act_warps / 2) {
     // ===================================== softmax / epilogue warps =====================================
-    const int tile = warp >> 2;
+    const int half = warp >> 3;                                     // which half of the words
+    const int tile = (warp >> 2) & 1;
     const int rg = tile * 128 + (warp & 3) * 32 + lane;             // region row owned by this thread
-    const uint32_t t_s = tmem_base + (((uint32_t)(warp & 3) * 32) << 16) + tile * NT;
-    const uint32_t t_m = t_s + L.tiles * NT;
+    const int c0 = half * NH;                                       // first word column owned by this thread
+    const uint32_t t_lane = tmem_base + (((uint32_t)(warp & 3) * 32) << 16) + tile * NT + c0;
+    const uint32_t t_m = t_lane + col_m;
     const bool valid = rg < R;
-    const bool k_row = rg < L.k2_steps * 16;                        // row is inside GEMM2's K range
-    uint8_t *e2_row = E2 + (rg >> 6) * (NT * 128);
-    const int rcol = rg & 63;
-    const uint32_t mw0 = maskw[0], mw1 = maskw[1], mw2 = maskw[2], mw3 = maskw[3];
-    auto mbit = [&](int t) -> bool {
-      const uint32_t w = t < 32 ? mw0 : (t < 64 ? mw1 : (t < 96 ? mw2 : mw3));
-      return (w >> (t & 31)) & 1u;
-    };
-    constexpr int NCH = (NT + 31) / 32;                            // 32-column chunks (last may be 16 wide)
+    const uint32_t rowmask = valid ? 0xffffffffu : 0u;
+    const bool k_row = rg < L.k2_steps * 16;                        // row lies inside GEMM2's K range
+    // shared-memory address of e2[t = c0][r' = rg] and the 8 swizzle variants (t & 7)
+    uint32_t e2a[8];
+    {
+      const uint32_t base = smem_u32(E2) + (uint32_t)(rg >> 6) * (NT * 128) + (uint32_t)c0 * 128 + ((rg & 7) << 1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) e2a[k] = base + (((((uint32_t)rg & 63) >> 3) ^ k) << 4);
+    }
+    const float4 *tb4 = reinterpret_cast<const float4 *>(tb + c0);
+    const float2 *tb22 = reinterpret_cast<const float2 *>(tb2 + c0);
+    const float4 *vch = vc + c0;
+    float *red1w = red1 + warp * NH, *red2w = red2 + warp * NH;
+    const int widx = (warp & 7) * 32 + lane;                        // row slot in zbuf / wbuf
+    const int sidx = (half * (L.act_warps / 2) + (warp & 7)) * 32 + lane;   // rank among the active softmax threads
     for (int j = j0, it = 0; j < j1; ++j, ++it) {
-      const uint32_t par = it & 1;
-      float e1[NT];
-      uint32_t e2p[NT / 2];
-      mbar_wait(s_full, par);
+      const int b = it % nbuf;
+      const uint32_t t_s = t_lane + (uint32_t)(b * L.tiles * NT);
+      float e1[NH];
+      uint32_t e2p[NH / 2];
+      mbar_wait(&s_full[b], (it / nbuf) & 1);
       tc_fence_after();
-      // ---- pass A: e1 = mask exp(S), Z = sum_t e1 (softmax over words, losses.py:127,143-144) ----
-      float Z = 0.f;
+      // ---- pass A: e1 = exp(S + mask bias), Z = sum_t e1 (softmax over words, losses.py:127,143-144) ----
+      float zp = 0.f;
 #pragma unroll
-      for (int c = 0; c < NT / 16; ++c) {
-        float x[16];
-        tmem_ld16(t_s + c * 16, x);
+      for (int c = 0; c < NH / 8; ++c) {
+        float x[8];
+        tmem_ld<8>(t_s + c * 8, x);
+        const float4 ba = tb4[2 * c], bb = tb4[2 * c + 1];
+        const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const int t = c * 16 + k;
-          const float e = mbit(t) ? __expf(x[k]) : 0.f;
-          e1[t] = e;
-          Z += e;
+        for (int k = 0; k < 8; ++k) {
+          const float e = ex2f(fmaf(x[k], kLog2e, bias[k]));
+          e1[c * 8 + k] = e;
+          zp += e;
         }
       }
+      zbuf[half * 256 + widx] = zp;
+      named_bar_sync(1, nsoft);
+      const float Z = zbuf[widx] + zbuf[256 + widx];
       const float invZ = 1.f / Z;
-      // ---- pass B: e2 = exp(gamma1 P) (softmax over regions, un-normalised), N' partial sums ----
+      const float k2 = p.g1 * kLog2e * invZ;
+      // ---- pass B: e2 = exp(gamma1 P) (softmax over regions, un-normalised) -> fp16 B operand; N' partials ----
+      auto pass_b = [&](auto width, auto cb) {
+        constexpr int W = decltype(width)::value;
+        constexpr int cbeg = decltype(cb)::value;
+        float x[W];
+        tmem_ld<W>(t_s + cbeg, x);
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        float x[32];
-        tmem_ld16(t_s + c * 32, x);
-        if (c * 32 + 16 < NT) tmem_ld16(t_s + c * 32 + 16, x + 16);
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const int t = c * 32 + k;
-          if (t < NT) {
-            float e2 = (valid && t < T) ? __expf(p.g1 * e1[t] * invZ) : 0.f;
-            const __half hb = __float2half_rn(e2);
-            e2 = __half2float(hb);                                  // the value the tensor core will see
-            if (k_row) *reinterpret_cast<__half *>(e2_row + sw128_offset(t, rcol)) = hb;
-            const uint32_t bits = (uint32_t)__half_as_ushort(hb);
-            if (t & 1) e2p[t >> 1] |= bits << 16; else e2p[t >> 1] = bits;
-            x[k] = valid ? e2 * x[k] : 0.f;                        // rows past the stage hold garbage
-          } else {
-            x[k] = 0.f;
+        for (int k = 0; k < W; k += 2) {
+          const int tl = cbeg + k;
+          const float2 bz = tb22[tl >> 1];
+          const float a0 = ex2f(fmaf(e1[tl], k2, bz.x));
+          const float a1 = ex2f(fmaf(e1[tl + 1], k2, bz.y));
+          const uint32_t h2 = pack_half2(a0, a1) & rowmask;        // rows >= R contribute nothing
+          e2p[tl >> 1] = h2;
+          if (k_row) {
+            sts_u16(e2a[tl & 7] + tl * 128, h2 & 0xffffu);
+            sts_u16(e2a[(tl + 1) & 7] + (tl + 1) * 128, h2 >> 16);
           }
+          const float2 f = unpack_half2(h2);                        // the values the tensor core will see
+          x[k] *= f.x;
+          x[k + 1] *= f.y;
         }
-        const float cs = warp_colsum32(x, lane);
-        if (c * 32 + lane < NT) red1[warp * NT + c * 32 + lane] = cs;
-      }
+        const float cs = warp_colsum<W>(x, lane);
+        if (lane < W) red1w[cbeg + lane] = cs;
+      };
+      if constexpr (NH >= 32) pass_b(std::integral_constant<int, 32>{}, std::integral_constant<int, 0>{});
+      if constexpr (NH == 64) pass_b(std::integral_constant<int, 32>{}, std::integral_constant<int, 32>{});
+      if constexpr (NH == 40) pass_b(std::integral_constant<int, 8>{}, std::integral_constant<int, 32>{});
+      if constexpr (NH == 16) pass_b(std::integral_constant<int, 16>{}, std::integral_constant<int, 0>{});
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(e2_ready);
-      if (!BWD) mbar_arrive(s_free);                               // forward: S is dead, GEMM1 of the next pair may start
+      if (!BWD) mbar_arrive(&s_free[b]);                            // forward: S is dead from here on
       // ---- after GEMM2: NN partial sums; the appended ones-row delivers Y_t ----
-      mbar_wait(m_full, par);
+      mbar_wait(m_full, it & 1);
       tc_fence_after();
+      auto pass_m = [&](auto width, auto cb) {
+        constexpr int W = decltype(width)::value;
+        constexpr int cbeg = decltype(cb)::value;
+        float x[W];
+        tmem_ld<W>(t_m + cbeg, x);
+        if (rg == R) {
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        float x[32];
-        tmem_ld16(t_m + c * 32, x);
-        if (c * 32 + 16 < NT) tmem_ld16(t_m + c * 32 + 16, x + 16);
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const int t = c * 32 + k;
-          if (t < NT) {
-            if (rg == R && t < T) vY[t] = x[k];
-            const uint32_t bits = (t & 1) ? (e2p[t >> 1] >> 16) : (e2p[t >> 1] & 0xffffu);
-            x[k] = valid ? __half2float(__ushort_as_half((unsigned short)bits)) * x[k] : 0.f;
-          } else {
-            x[k] = 0.f;
-          }
+          for (int k = 0; k < W; ++k) vY[c0 + cbeg + k] = x[k];
         }
-        const float cs = warp_colsum32(x, lane);
-        if (c * 32 + lane < NT) red2[warp * NT + c * 32 + lane] = cs;
-      }
+#pragma unroll
+        for (int k = 0; k < W; k += 2) {
+          const float2 f = unpack_half2(e2p[(cbeg + k) >> 1]);
+          x[k] *= f.x;
+          x[k + 1] *= f.y;
+        }
+        const float cs = warp_colsum<W>(x, lane);
+        if (lane < W) red2w[cbeg + lane] = cs;
+      };
+      if constexpr (NH >= 32) pass_m(std::integral_constant<int, 32>{}, std::integral_constant<int, 0>{});
+      if constexpr (NH == 64) pass_m(std::integral_constant<int, 32>{}, std::integral_constant<int, 32>{});
+      if constexpr (NH == 40) pass_m(std::integral_constant<int, 8>{}, std::integral_constant<int, 32>{});
+      if constexpr (NH == 16) pass_m(std::integral_constant<int, 16>{}, std::integral_constant<int, 0>{});
       if (!BWD) { tc_fence_before(); mbar_arrive(m_free); }
       named_bar_sync(1, nsoft);
       // ---- per-word cosine (losses.py:197-198) and gamma2 log-sum-exp (:199-203) ----
-      if ((int)threadIdx.x < T) {
-        const int t = threadIdx.x;
+      for (int t = sidx; t < T; t += nsoft) {
+        const int h = t / NH, tl = t - h * NH;
         float np = 0.f, nn = 0.f;
-        for (int w = 0; w < L.tiles * 4; ++w) { np += red1[w * NT + t]; nn += red2[w * NT + t]; }
+        for (int w = 0; w < L.act_warps / 2; ++w) {
+          np += red1[(h * 8 + w) * NH + tl];
+          nn += red2[(h * 8 + w) * NH + tl];
+        }
         const float y = vY[t];
         const float n = sqrtf(fmaxf(nn, 0.f)) / y;
         const float rho = (np / y) / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
@@ -314,97 +439,89 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
-      // red1/red2/vxs of this pair must be consumed before the next pair's pass B overwrites them
-      named_bar_sync(1, nsoft);
+      // The next pair's zbuf barrier orders this pair's reads of red1/red2/vxs/vY before they are rewritten.
       if (BWD) {
+        named_bar_sync(1, nsoft);
         // ---- per-word backward coefficients: beta = dL/drho, a = beta/(n u), b = beta rho / n^2 ----
-        if ((int)threadIdx.x < T) {
-          const int t = threadIdx.x;
+        for (int t = sidx; t < T; t += nsoft) {
           const float omega = __expf(vxs[t] - vmisc[0]);
           const float beta = vmisc[1] * p.g3 * omega;
           const float n = vn[t], rho = vrho[t], iy = viy[t];
           const float a = beta / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
-          const float b = (n > kCosEps) ? beta * rho / (n * n) : 0.f;
-          vc[t] = make_float4(p.g1 * a * iy, p.g1 * b * iy * iy, a * iy, b * iy);
+          const float bq = (n > kCosEps) ? beta * rho / (n * n) : 0.f;
+          vc[t] = make_float4(p.g1 * a * iy, p.g1 * bq * iy * iy, a * iy * p.scale_ds, bq * iy * p.scale_ba);
           atomicAdd(p.kq + (int64_t)i * T + t, beta * rho);
         }
         named_bar_sync(1, nsoft);
-        // ---- dS = a A + P (dP - W), dP = gamma1 A (a S - b M), W = sum_t P dP (in-thread: this row's words) ----
-        float W = 0.f;
+        // ---- W = sum_t P dP with dP = gamma1 A (a S - b M)  (this row, all words: two halves via wbuf) ----
+        float wp = 0.f;
 #pragma unroll
-        for (int c = 0; c < NT / 16; ++c) {
-          float xs[16], xm[16];
-          tmem_ld16(t_s + c * 16, xs);
-          tmem_ld16(t_m + c * 16, xm);
+        for (int c = 0; c < NH / 8; ++c) {
+          float xs[8], xm[8];
+          tmem_ld<8>(t_s + c * 8, xs);
+          tmem_ld<8>(t_m + c * 8, xm);
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const int t = c * 16 + k;
-            const uint32_t bits = (t & 1) ? (e2p[t >> 1] >> 16) : (e2p[t >> 1] & 0xffffu);
-            const float e2 = __half2float(__ushort_as_half((unsigned short)bits));
-            const float4 cf = vc[t];
-            const float dP = e2 * (cf.x * xs[k] - cf.y * xm[k]);
-            if (t < T) W = fmaf(e1[t] * invZ, dP, W);
+          for (int k = 0; k < 8; k += 2) {
+            const int tl = c * 8 + k;
+            const float2 f = unpack_half2(e2p[tl >> 1]);
+            const float4 ca = vch[tl], cb = vch[tl + 1];
+            wp = fmaf(e1[tl], f.x * (ca.x * xs[k] - ca.y * xm[k]), wp);
+            wp = fmaf(e1[tl + 1], f.y * (cb.x * xs[k + 1] - cb.y * xm[k + 1]), wp);
           }
         }
+        wbuf[half * 256 + widx] = wp * invZ;
+        named_bar_sync(1, nsoft);
+        const float Wr = wbuf[widx] + wbuf[256 + widx];
+        // ---- dS = a A + P (dP - W); A; diag(b) A  -> scaled fp16 rows of the scratch matrices ----
         {
-          // tcgen05.ld is warp-collective (.sync.aligned): every lane executes the loads, only the stores of
-          // rows that exist (rg < R) are predicated
           const int64_t row = (int64_t)j * R + (valid ? rg : 0);
-          const int64_t off = row * p.kc + (int64_t)blockIdx.x * p.tp;
+          const int64_t off = row * p.kc + (int64_t)blockIdx.x * p.tp + c0;
           uint4 *o_ds = reinterpret_cast<uint4 *>(p.x_ds + off);
           uint4 *o_a = reinterpret_cast<uint4 *>(p.x_a + off);
           uint4 *o_ba = reinterpret_cast<uint4 *>(p.x_ba + off);
+          const float sp = p.scale_ds * invZ;
 #pragma unroll
-          for (int c = 0; c < NT / 16; ++c) {
-            if (c * 16 < p.tp) {
-              float xs[16], xm[16];
-              tmem_ld16(t_s + c * 16, xs);
-              tmem_ld16(t_m + c * 16, xm);
-              uint32_t pk_ds[8], pk_a[8], pk_ba[8];
+          for (int c = 0; c < NH / 8; ++c) {
+            if (c0 + c * 8 < p.tp) {                                 // warp-uniform: tcgen05.ld is warp-collective
+              float xs[8], xm[8];
+              tmem_ld<8>(t_s + c * 8, xs);
+              tmem_ld<8>(t_m + c * 8, xm);
+              uint32_t pk_ds[4], pk_a[4], pk_ba[4];
 #pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                const int t = c * 16 + k;
-                const uint32_t bits = (t & 1) ? (e2p[t >> 1] >> 16) : (e2p[t >> 1] & 0xffffu);
-                const float e2 = __half2float(__ushort_as_half((unsigned short)bits));
-                const float4 cf = vc[t];
-                const float dP = e2 * (cf.x * xs[k] - cf.y * xm[k]);
-                float ds = 0.f, av = 0.f, bav = 0.f;
-                if (t < T) {
-                  ds = p.scale_ds * fmaf(cf.z, e2, e1[t] * invZ * (dP - W));
-                  av = viy[t] * e2;
-                  bav = p.scale_ba * cf.w * e2;
-                  ds = fminf(fmaxf(ds, -65504.f), 65504.f);
-                  bav = fminf(fmaxf(bav, -65504.f), 65504.f);
-                }
-                const uint32_t h_ds = __half_as_ushort(__float2half_rn(ds));
-                const uint32_t h_a = __half_as_ushort(__float2half_rn(av));
-                const uint32_t h_ba = __half_as_ushort(__float2half_rn(bav));
-                if (k & 1) { pk_ds[k >> 1] |= h_ds << 16; pk_a[k >> 1] |= h_a << 16; pk_ba[k >> 1] |= h_ba << 16; }
-                else       { pk_ds[k >> 1] = h_ds;        pk_a[k >> 1] = h_a;        pk_ba[k >> 1] = h_ba; }
+              for (int k = 0; k < 8; k += 2) {
+                const int tl = c * 8 + k;
+                const float2 f = unpack_half2(e2p[tl >> 1]);
+                const float4 ca = vch[tl], cb = vch[tl + 1];
+                const float dp0 = f.x * (ca.x * xs[k] - ca.y * xm[k]);
+                const float dp1 = f.y * (cb.x * xs[k + 1] - cb.y * xm[k + 1]);
+                float ds0 = fmaf(ca.z, f.x, sp * e1[tl] * (dp0 - Wr));
+                float ds1 = fmaf(cb.z, f.y, sp * e1[tl + 1] * (dp1 - Wr));
+                float ba0 = ca.w * f.x, ba1 = cb.w * f.y;
+                ds0 = fminf(fmaxf(ds0, -65504.f), 65504.f);
+                ds1 = fminf(fmaxf(ds1, -65504.f), 65504.f);
+                ba0 = fminf(fmaxf(ba0, -65504.f), 65504.f);
+                ba1 = fminf(fmaxf(ba1, -65504.f), 65504.f);
+                pk_ds[k >> 1] = pack_half2(ds0, ds1);
+                pk_a[k >> 1] = pack_half2(viy[c0 + tl] * f.x, viy[c0 + tl + 1] * f.y);
+                pk_ba[k >> 1] = pack_half2(ba0, ba1);
               }
               if (valid) {
-                o_ds[2 * c] = make_uint4(pk_ds[0], pk_ds[1], pk_ds[2], pk_ds[3]);
-                o_a[2 * c] = make_uint4(pk_a[0], pk_a[1], pk_a[2], pk_a[3]);
-                o_ba[2 * c] = make_uint4(pk_ba[0], pk_ba[1], pk_ba[2], pk_ba[3]);
-                if (c * 16 + 8 < p.tp) {
-                  o_ds[2 * c + 1] = make_uint4(pk_ds[4], pk_ds[5], pk_ds[6], pk_ds[7]);
-                  o_a[2 * c + 1] = make_uint4(pk_a[4], pk_a[5], pk_a[6], pk_a[7]);
-                  o_ba[2 * c + 1] = make_uint4(pk_ba[4], pk_ba[5], pk_ba[6], pk_ba[7]);
-                }
+                o_ds[c] = make_uint4(pk_ds[0], pk_ds[1], pk_ds[2], pk_ds[3]);
+                o_a[c] = make_uint4(pk_a[0], pk_a[1], pk_a[2], pk_a[3]);
+                o_ba[c] = make_uint4(pk_ba[0], pk_ba[1], pk_ba[2], pk_ba[3]);
               }
             }
           }
         }
         tc_fence_before();
-        mbar_arrive(s_free);
+        mbar_arrive(&s_free[b]);
         mbar_arrive(m_free);
-        named_bar_sync(1, nsoft);      // vc / viy are rewritten by the next pair
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem_base);
+  if (warp == 17) tmem_dealloc<512>(tmem_base);
 }
 
 // ----------------------------------------------------------------------------------------------- host side
@@ -424,9 +541,9 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// 16-bit tensor (n2, n1, n0) contiguous except for the given row pitch; box (1, box1, 64), 128-byte swizzle
+// fp16 tensor (n2, n1, n0), rows `pitch1` and slabs `pitch2` elements apart; box (1, box1, 64), 128-byte swizzle
 static int make_map_f16(CUtensorMap *m, const void *base, uint64_t n0, uint64_t n1, uint64_t n2, uint64_t pitch1_elems,
-                         uint64_t pitch2_elems, uint32_t box1) {
+                        uint64_t pitch2_elems, uint32_t box1) {
   PFN_encodeTiled enc = get_encode();
   DAMSM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[3] = {n0, n1, n2};
@@ -449,14 +566,6 @@ static int pick_nt(int T) {
   return -1;
 }
 
-}  // namespace damsm
-
-using namespace damsm;
-
-extern "C" int64_t damsm_words_tc_gx_cols(int64_t r) { return (r + 63) / 64 * 64; }
-
-// Gx (bc, R+1, RK) bf16 from the fp32 Gram matrices: zero-padded columns, appended row of ones.
-namespace damsm {
 __global__ void __launch_bounds__(256) gram_pack_f16_kernel(const float *__restrict__ gram, int R, int RK,
                                                             __half *__restrict__ gx) {
   const int j = blockIdx.x;
@@ -469,76 +578,62 @@ __global__ void __launch_bounds__(256) gram_pack_f16_kernel(const float *__restr
     o[e] = __float2half_rn(v);
   }
 }
-}  // namespace damsm
 
-extern "C" int damsm_gram_pack_tc(const float *gram, int64_t bc, int64_t r, void *gx, void *stream) {
-  DAMSM_REQUIRE(gram && gx && r > 0, "gram_pack_tc: bad arguments");
-  if (bc == 0) return 0;
-  gram_pack_f16_kernel<<<(unsigned)bc, 256, 0, (cudaStream_t)stream>>>(gram, (int)r, (int)damsm_words_tc_gx_cols(r),
-                                                                       (__half *)gx);
-  return check_launch("gram_pack_tc");
-}
+struct TcLaunch {
+  int nt;
+  TcLayout L;
+  CUtensorMap tmQ, tmV, tmG;
+  int sms;
+};
 
-extern "C" int64_t damsm_words_tc_smem_bytes(int64_t t, int64_t r, int64_t d) {
-  const int nt = pick_nt((int)t);
-  if (nt < 0 || r < 1 || r > 255 || d < 64 || d % 64) return -1;
-  return tc_layout(nt, (int)r, (int)d).total;
-}
-
-extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
-                                    const float *unorm, const uint8_t *mask, int64_t br, int64_t bc, int64_t t,
-                                    int64_t r, int64_t d, float gamma1, float gamma2, float gamma3, float *sim,
-                                    void *stream) {
-  DAMSM_REQUIRE(qhat16 && vhat16 && gx && unorm && mask && sim, "words_fwd_tc: null pointer");
-  const int nt = pick_nt((int)t);
-  DAMSM_REQUIRE(nt > 0, "words_fwd_tc: T=%lld outside [1,128]", (long long)t);
-  DAMSM_REQUIRE(r >= 1 && r <= 255, "words_fwd_tc: R=%lld outside [1,255]", (long long)r);
-  DAMSM_REQUIRE(d >= 64 && d % 64 == 0, "words_fwd_tc: D=%lld must be a multiple of 64", (long long)d);
-  if (br == 0 || bc == 0) return 0;
-  const TcLayout L = tc_layout(nt, (int)r, (int)d);
-  int dev = 0, max_optin = 0, sms = 0;
+static int tc_prepare(TcLaunch *tl, const char *who, const void *qhat16, int64_t q_rows, const void *vhat16,
+                      const void *gx, int64_t br, int64_t bc, int64_t t, int64_t r, int64_t d) {
+  tl->nt = pick_nt((int)t);
+  DAMSM_REQUIRE(tl->nt > 0, "%s: T=%lld outside [1,128]", who, (long long)t);
+  DAMSM_REQUIRE(r >= 1 && r <= 255, "%s: R=%lld outside [1,255]", who, (long long)r);
+  DAMSM_REQUIRE(d >= 64 && d % 64 == 0, "%s: D=%lld must be a multiple of 64", who, (long long)d);
+  DAMSM_REQUIRE(q_rows >= t, "%s: q_rows < T", who);
+  tl->L = tc_layout(tl->nt, (int)r, (int)d);
+  int dev = 0, max_optin = 0;
   DAMSM_CUDA(cudaGetDevice(&dev));
   DAMSM_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  DAMSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  DAMSM_REQUIRE((int64_t)L.total <= max_optin,
-                "words_fwd_tc: T=%lld R=%lld needs %u B of shared memory (> %d)", (long long)t, (long long)r, L.total,
-                max_optin);
-  const int64_t rk = damsm_words_tc_gx_cols(r);
-  CUtensorMap tmQ, tmV, tmG;
+  DAMSM_CUDA(cudaDeviceGetAttribute(&tl->sms, cudaDevAttrMultiProcessorCount, dev));
+  DAMSM_REQUIRE((int64_t)tl->L.total <= max_optin, "%s: T=%lld R=%lld needs %u B of shared memory (> %d)", who,
+                (long long)t, (long long)r, tl->L.total, max_optin);
+  const int64_t rk = (r + 63) / 64 * 64;
   int rc;
-  DAMSM_REQUIRE(q_rows >= t, "words_fwd_tc: q_rows < T");
-  if ((rc = make_map_f16(&tmQ, qhat16, d, q_rows, br, d, q_rows * d, nt))) return rc;
-  if ((rc = make_map_f16(&tmV, vhat16, d, r, bc, d, r * d, L.rs))) return rc;
-  if ((rc = make_map_f16(&tmG, gx, rk, r + 1, bc, rk, (r + 1) * rk, L.rs))) return rc;
-  TcParams p{};
-  p.br = (int)br; p.bc = (int)bc; p.T = (int)t; p.R = (int)r; p.D = (int)d;
-  p.g1 = gamma1; p.g2 = gamma2; p.g3 = gamma3; p.mask = mask; p.unorm = unorm; p.sim = sim;
+  if ((rc = make_map_f16(&tl->tmQ, qhat16, d, q_rows, br, d, q_rows * d, tl->nt))) return rc;
+  if ((rc = make_map_f16(&tl->tmV, vhat16, d, r, bc, d, r * d, tl->L.rs))) return rc;
+  if ((rc = make_map_f16(&tl->tmG, gx, rk, r + 1, bc, rk, (r + 1) * rk, tl->L.rs))) return rc;
+  return 0;
+}
+
+template <bool BWD>
+static int tc_launch(const TcLaunch &tl, TcParams &p, int64_t rows, cudaStream_t st) {
   // split the image range so that the grid covers the SMs a few times over
-  int splits = (int)((4LL * sms + br - 1) / br);
+  int splits = (int)((4LL * tl.sms + rows - 1) / rows);
   if (splits < 1) splits = 1;
-  if (splits > bc) splits = (int)bc;
-  p.img_per_cta = (int)((bc + splits - 1) / splits);
-  splits = (int)((bc + p.img_per_cta - 1) / p.img_per_cta);
-  DAMSM_REQUIRE(br <= 2147483647 && splits <= 65535, "words_fwd_tc: grid too large");
-  dim3 grid((unsigned)br, (unsigned)splits);
-  cudaStream_t st = (cudaStream_t)stream;
-#define DAMSM_LAUNCH_TC(NT_)                                                                                         \
-  do {                                                                                                               \
-    DAMSM_CUDA(cudaFuncSetAttribute(words_tc_kernel<NT_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
-    words_tc_kernel<NT_, false><<<grid, TC_THREADS, L.total, st>>>(tmQ, tmV, tmG, p);                                \
+  if (splits > p.bc) splits = p.bc;
+  p.img_per_cta = (p.bc + splits - 1) / splits;
+  splits = (p.bc + p.img_per_cta - 1) / p.img_per_cta;
+  DAMSM_REQUIRE(rows <= 2147483647 && splits <= 65535, "tensor-core launch: grid too large");
+  dim3 grid((unsigned)rows, (unsigned)splits);
+#define DAMSM_LAUNCH_TC(NT_)                                                                                          \
+  do {                                                                                                                \
+    DAMSM_CUDA(cudaFuncSetAttribute(words_tc_kernel<NT_, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                    (int)tl.L.total));                                                                \
+    words_tc_kernel<NT_, BWD><<<grid, TC_THREADS, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, p);                       \
   } while (0)
-  switch (nt) {
+  switch (tl.nt) {
     case 32: DAMSM_LAUNCH_TC(32); break;
     case 64: DAMSM_LAUNCH_TC(64); break;
     case 80: DAMSM_LAUNCH_TC(80); break;
     default: DAMSM_LAUNCH_TC(128); break;
   }
 #undef DAMSM_LAUNCH_TC
-  return check_launch("words_fwd_tc");
+  return check_launch(BWD ? "words_bwd_tc (fused recompute)" : "words_fwd_tc");
 }
 
-// ----------------------------------------------------------------------------------------------- backward driver
-namespace damsm {
 static cublasHandle_t get_cublas() {
   static thread_local cublasHandle_t h = nullptr;
   if (!h && cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) h = nullptr;
@@ -552,49 +647,67 @@ static cublasHandle_t get_cublas() {
       return 4;                                                               \
     }                                                                         \
   } while (0)
+
 }  // namespace damsm
 
-// bytes of scratch per caption row of a chunk: three bf16 matrices [(j,r)][t_pad]
+using namespace damsm;
+
+extern "C" int64_t damsm_words_tc_gx_cols(int64_t r) { return (r + 63) / 64 * 64; }
+
+extern "C" int damsm_gram_pack_tc(const float *gram, int64_t bc, int64_t r, void *gx, void *stream) {
+  DAMSM_REQUIRE(gram && gx && r > 0, "gram_pack_tc: bad arguments");
+  if (bc == 0) return 0;
+  gram_pack_f16_kernel<<<(unsigned)bc, 256, 0, (cudaStream_t)stream>>>(gram, (int)r, (int)damsm_words_tc_gx_cols(r),
+                                                                      (__half *)gx);
+  return check_launch("gram_pack_tc");
+}
+
+extern "C" int64_t damsm_words_tc_smem_bytes(int64_t t, int64_t r, int64_t d) {
+  const int nt = pick_nt((int)t);
+  if (nt < 0 || r < 1 || r > 255 || d < 64 || d % 64) return -1;
+  return tc_layout(nt, (int)r, (int)d).total;
+}
+
+extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
+                                  const float *unorm, const uint8_t *mask, int64_t br, int64_t bc, int64_t t, int64_t r,
+                                  int64_t d, float gamma1, float gamma2, float gamma3, float *sim, void *stream) {
+  DAMSM_REQUIRE(qhat16 && vhat16 && gx && unorm && mask && sim, "words_fwd_tc: null pointer");
+  if (br == 0 || bc == 0) return 0;
+  TcLaunch tl;
+  int rc;
+  if ((rc = tc_prepare(&tl, "words_fwd_tc", qhat16, q_rows, vhat16, gx, br, bc, t, r, d))) return rc;
+  TcParams p{};
+  p.br = (int)br; p.bc = (int)bc; p.T = (int)t; p.R = (int)r; p.D = (int)d;
+  p.g1 = gamma1; p.g2 = gamma2; p.g3 = gamma3; p.mask = mask; p.unorm = unorm; p.sim = sim;
+  return tc_launch<false>(tl, p, br, (cudaStream_t)stream);
+}
+
+// bytes of scratch per caption row of a chunk: three fp16 matrices [(j,r)][t_pad]
 extern "C" int64_t damsm_words_bwd_tc_row_bytes(int64_t bc, int64_t t, int64_t r) {
   const int64_t tp = (t + 7) / 8 * 8;
   return 3 * tp * bc * r * 2;
 }
 
 extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
-                                    const float *unorm, const uint8_t *mask, const float *sim, const float *row_lse,
-                                    const float *col_lse, const int64_t *labels, const float *gscale,
-                                    int64_t row_offset, int64_t b_total, int64_t br, int64_t bc, int64_t t, int64_t r,
-                                    int64_t d, float gamma1, float gamma2, float gamma3, void *workspace,
-                                    int64_t workspace_bytes, float *dqhat, float *dvhat, float *hmat, float *kq,
-                                    void *stream) {
+                                  const float *unorm, const uint8_t *mask, const float *sim, const float *row_lse,
+                                  const float *col_lse, const int64_t *labels, const float *gscale, int64_t row_offset,
+                                  int64_t b_total, int64_t br, int64_t bc, int64_t t, int64_t r, int64_t d, float gamma1,
+                                  float gamma2, float gamma3, void *workspace, int64_t workspace_bytes, float *dqhat,
+                                  float *dvhat, float *hmat, float *kq, void *stream) {
   DAMSM_REQUIRE(qhat16 && vhat16 && gx && unorm && mask && sim && row_lse && col_lse && gscale && workspace && dqhat &&
                     dvhat && hmat && kq, "words_bwd_tc: null pointer");
-  const int nt = pick_nt((int)t);
-  DAMSM_REQUIRE(nt > 0, "words_bwd_tc: T=%lld outside [1,128]", (long long)t);
-  DAMSM_REQUIRE(r >= 1 && r <= 255, "words_bwd_tc: R=%lld outside [1,255]", (long long)r);
-  DAMSM_REQUIRE(d >= 64 && d % 64 == 0, "words_bwd_tc: D=%lld must be a multiple of 64", (long long)d);
   const int64_t tp = (t + 7) / 8 * 8;
-  DAMSM_REQUIRE(q_rows == tp, "words_bwd_tc: qhat16 must be padded to %lld rows per caption (got %lld)",
-                (long long)tp, (long long)q_rows);
+  DAMSM_REQUIRE(q_rows == tp, "words_bwd_tc: qhat16 must be padded to %lld rows per caption (got %lld)", (long long)tp,
+                (long long)q_rows);
   if (br == 0 || bc == 0) return 0;
+  TcLaunch tl;
+  int rc;
+  if ((rc = tc_prepare(&tl, "words_bwd_tc", qhat16, q_rows, vhat16, gx, br, bc, t, r, d))) return rc;
   const int64_t row_bytes = damsm_words_bwd_tc_row_bytes(bc, t, r);
   int64_t chunk = workspace_bytes / row_bytes;
   DAMSM_REQUIRE(chunk >= 1, "words_bwd_tc: workspace of %lld B is smaller than one caption row (%lld B)",
                 (long long)workspace_bytes, (long long)row_bytes);
   if (chunk > br) chunk = br;
-  const TcLayout L = tc_layout(nt, (int)r, (int)d);
-  int dev = 0, max_optin = 0, sms = 0;
-  DAMSM_CUDA(cudaGetDevice(&dev));
-  DAMSM_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  DAMSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  DAMSM_REQUIRE((int64_t)L.total <= max_optin, "words_bwd_tc: T=%lld R=%lld needs %u B of shared memory (> %d)",
-                (long long)t, (long long)r, L.total, max_optin);
-  const int64_t rk = damsm_words_tc_gx_cols(r);
-  CUtensorMap tmQ, tmV, tmG;
-  int rc;
-  if ((rc = make_map_f16(&tmQ, qhat16, d, q_rows, br, d, q_rows * d, nt))) return rc;
-  if ((rc = make_map_f16(&tmV, vhat16, d, r, bc, d, r * d, L.rs))) return rc;
-  if ((rc = make_map_f16(&tmG, gx, rk, r + 1, bc, rk, (r + 1) * rk, L.rs))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   cublasHandle_t h = get_cublas();
   DAMSM_REQUIRE(h != nullptr, "words_bwd_tc: cublasCreate failed");
@@ -619,25 +732,7 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
     p.i0 = (int)i0; p.tp = (int)tp; p.kc = kc; p.row_lse = row_lse; p.col_lse = col_lse; p.gscale = gscale;
     p.labels = labels; p.row_offset = row_offset; p.b_total = b_total; p.kq = kq;
     p.x_ds = x_ds; p.x_a = x_a; p.x_ba = x_ba; p.scale_ds = scale_ds; p.scale_ba = scale_ba;
-    int splits = (int)((4LL * sms + bi - 1) / bi);
-    if (splits < 1) splits = 1;
-    if (splits > bc) splits = (int)bc;
-    p.img_per_cta = (int)((bc + splits - 1) / splits);
-    splits = (int)((bc + p.img_per_cta - 1) / p.img_per_cta);
-    dim3 grid((unsigned)bi, (unsigned)splits);
-#define DAMSM_LAUNCH_TCB(NT_)                                                                                        \
-  do {                                                                                                               \
-    DAMSM_CUDA(cudaFuncSetAttribute(words_tc_kernel<NT_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
-    words_tc_kernel<NT_, true><<<grid, TC_THREADS, L.total, st>>>(tmQ, tmV, tmG, p);                                 \
-  } while (0)
-    switch (nt) {
-      case 32: DAMSM_LAUNCH_TCB(32); break;
-      case 64: DAMSM_LAUNCH_TCB(64); break;
-      case 80: DAMSM_LAUNCH_TCB(80); break;
-      default: DAMSM_LAUNCH_TCB(128); break;
-    }
-#undef DAMSM_LAUNCH_TCB
-    if ((rc = check_launch("words_bwd_tc (fused recompute)"))) return rc;
+    if ((rc = tc_launch<true>(tl, p, bi, st))) return rc;
     if (getenv("DAMSM_DEBUG_SYNC")) {
       cudaError_t e = cudaStreamSynchronize(st);
       fprintf(stderr, "damsm debug: fused bwd kernel chunk i0=%lld done: %s\n", (long long)i0, cudaGetErrorString(e));
