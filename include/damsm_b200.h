@@ -106,12 +106,15 @@ DAMSM_API int64_t damsm_words_tc_gx_cols(int64_t r);
 DAMSM_API int damsm_gram_pack_tc(const float *gram, int64_t bc, int64_t r, void *gx, void *stream);
 /* host: dynamic shared memory of the tcgen05 kernel for (T,R,D); <0 if the shape is unsupported */
 DAMSM_API int64_t damsm_words_tc_smem_bytes(int64_t t, int64_t r, int64_t d);
-/* q_rows = rows per caption in qhat16 (T, or T padded to a multiple of 8 with zero rows) */
+/* q_rows = rows per caption in qhat16 (T, or T padded to a multiple of 8 with zero rows).
+ * stats (br, bc, 3, T) fp32 or NULL: per pair and word the cosine rho_t, ||c_t|| and 1/Y_t that the backward
+ * needs (12*T bytes per pair; B^2*T, not B^2*T*R). */
 DAMSM_API int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
-                                   const float *unorm, const uint8_t *mask, int64_t br, int64_t bc, int64_t t,
-                                   int64_t r, int64_t d, float gamma1, float gamma2, float gamma3, float *sim,
-                                   void *stream);
-/* Backward of the tensor-core path.  A fused tcgen05 kernel recomputes S, P, A, M per pair on chip and emits
+                                 const float *unorm, const uint8_t *mask, int64_t br, int64_t bc, int64_t t,
+                                 int64_t r, int64_t d, float gamma1, float gamma2, float gamma3, float *sim,
+                                 float *stats, void *stream);
+/* Backward of the tensor-core path.  A fused tcgen05 kernel recomputes S, P, A, M per pair on chip (the per-word
+ * scalars come from `stats` written by damsm_words_fwd_tc) and emits
  * dS, A and diag(b)A as (scaled) fp16 into `workspace`, one chunk of caption rows at a time
  * (damsm_words_bwd_tc_row_bytes() bytes per caption row; at least one row must fit); three plain GEMMs per
  * chunk (cuBLAS, fp16 in / fp32 accumulate) then contract them with qhat / vhat / each other:
@@ -120,8 +123,9 @@ DAMSM_API int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void 
  * qhat16 must be padded: q_rows == T rounded up to a multiple of 8. */
 DAMSM_API int64_t damsm_words_bwd_tc_row_bytes(int64_t bc, int64_t t, int64_t r);
 DAMSM_API int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
-                                   const float *unorm, const uint8_t *mask, const float *sim, const float *row_lse,
-                                   const float *col_lse, const int64_t *labels, const float *gscale,
+                                   const float *unorm, const uint8_t *mask, const float *sim, const float *stats,
+                                   const float *row_lse, const float *col_lse, const int64_t *labels,
+                                   const float *gscale,
                                    int64_t row_offset, int64_t b_total, int64_t br, int64_t bc, int64_t t, int64_t r,
                                    int64_t d, float gamma1, float gamma2, float gamma3, void *workspace,
                                    int64_t workspace_bytes, float *dqhat, float *dvhat, float *hmat, float *kq,

@@ -31,9 +31,9 @@ SIGNATURES = {
     "damsm_words_tc_gx_cols": [_l],
     "damsm_gram_pack_tc": [_p, _l, _l, _p, _p],
     "damsm_words_tc_smem_bytes": [_l, _l, _l],
-    "damsm_words_fwd_tc": [_p, _l, _p, _p, _p, _p, _l, _l, _l, _l, _l, _f, _f, _f, _p, _p],
+    "damsm_words_fwd_tc": [_p, _l, _p, _p, _p, _p, _l, _l, _l, _l, _l, _f, _f, _f, _p, _p, _p],
     "damsm_words_bwd_tc_row_bytes": [_l, _l, _l],
-    "damsm_words_bwd_tc": [_p, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _l, _l, _l, _f, _f, _f,
+    "damsm_words_bwd_tc": [_p, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _l, _l, _l, _f, _f, _f,
                              _p, _l, _p, _p, _p, _p, _p],
     "damsm_ce_stats_f32": [_p, _p, _p, _l, _l, _l, _p, _p, _p, _p],
     "damsm_ce_losses_f32": [_p, _p, _p, _p, _l, _l, _l, _l, _p, _p],

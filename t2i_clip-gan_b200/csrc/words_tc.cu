@@ -26,7 +26,6 @@
 namespace damsm {
 using namespace tc;
 
-constexpr int TC_THREADS = 576;
 constexpr int TC_STAGES = 3;
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -58,9 +57,9 @@ __host__ __device__ inline TcLayout tc_layout(int NT, int R, int D) {
   // the overrun of the last stage may reach into the e2 buffer but not into the fp32 bookkeeping behind it.
   if ((uint32_t)l.tiles * 16384 > l.stage_bytes + l.e2_bytes) l.stage_bytes = (uint32_t)l.tiles * 16384;
   l.misc_off = l.q_bytes + TC_STAGES * l.stage_bytes + l.e2_bytes;
-  // misc: 256 B of barriers / scalars, then floats: u,Y,xs,rho,n,iy,tb,tb2 [NT] + vc float4 [NT] +
-  // red1/red2 [16][NT/2] + zbuf/wbuf [2][256]
-  l.total = l.misc_off + 256 + 4 * (8 * NT + 4 * NT + 16 * NT + 1024) + 1024 /*alignment slack*/;
+  // misc: 256 B of barriers / scalars, then floats: u,tb,tb2 [NT] + iy,Y [2][NT] + vc float4 [2][NT] +
+  // red1/red2 [2][16][NT/2] + zbuf/wbuf [2][256]   ([2] = double-buffered by pair parity)
+  l.total = l.misc_off + 256 + 4 * (7 * NT + 8 * NT + 32 * NT + 1024) + 1024 /*alignment slack*/;
   return l;
 }
 
@@ -71,6 +70,7 @@ struct TcParams {
   const uint8_t *mask;
   const float *unorm;
   float *sim;          // forward: out (br, bc); backward: in (masked, gamma3-scaled)
+  float *stats;        // (br, bc, 3, T): rho, ||c||, 1/Y per word; forward writes (may be NULL), backward reads
   // ---- backward only ----
   int i0;              // first caption row of this chunk (blockIdx.x is relative to it)
   int tp;              // T padded to a multiple of 8: words per caption in the scratch matrices
@@ -96,8 +96,30 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {   // saturates to +-65504 instead of inf
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ float2 unpack_half2(uint32_t v) {
   return __half22float2(*reinterpret_cast<const __half2 *>(&v));
+}
+
+// Issue-only TMEM load of 8 columns; pair with tmem_wait16() which also pins the data dependency.
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, float *v) {
+  uint32_t *r = reinterpret_cast<uint32_t *>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait16(float *a, float *b) {   // a[8], b[8] were loaded by tmem_ld8_issue
+  uint32_t *x = reinterpret_cast<uint32_t *>(a), *y = reinterpret_cast<uint32_t *>(b);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]),
+                 "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7])
+               :
+               : "memory");
 }
 
 // TMEM -> registers, N consecutive fp32 columns of this thread's lane
@@ -142,11 +164,16 @@ __device__ __forceinline__ float warp_colsum(float (&v)[N], int lane) {
   return v[0];
 }
 
-template <int NT, bool BWD>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// NW = 16: the two softmax warps that own no region row (R+1 <= 224) serve as TMA producer (warp 7) and MMA
+// issuer (warp 15), 4 warps per scheduler and 128 registers per thread; NW = 18: two extra warps take those roles.
+template <int NT, bool BWD, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
                 const __grid_constant__ CUtensorMap tmG, TcParams p) {
   constexpr int NH = NT / 2;                 // words per softmax thread
+  constexpr int TC_THREADS = NW * 32;
+  constexpr int TMA_WARP = (NW == 16) ? 7 : 16;
+  constexpr int MMA_WARP = (NW == 16) ? 15 : 17;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const TcLayout L = tc_layout(NT, p.R, p.D);
@@ -161,14 +188,13 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t *s_free = q_full + 3;                      // 9,10
   uint64_t *e2_ready = q_full + 5, *m_full = q_full + 6, *m_free = q_full + 7;   // 11,12,13
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 16);
-  float *vmisc = reinterpret_cast<float *>(tmem_ptr + 4);    // [0] = lse, [1] = g_ij
   float *vu = reinterpret_cast<float *>(misc + 256);          // [NT] ||qhat_t||
-  float *vY = vu + NT, *vxs = vY + NT, *vrho = vxs + NT, *vn = vrho + NT, *viy = vn + NT;
-  float *tb = viy + NT;                                       // 0 for real words, -inf for padding and t >= T
+  float *tb = vu + NT;                                        // 0 for real words, -inf for padding and t >= T
   float *tb2 = tb + NT;                                       // 0 for t < T, -inf for t >= T
-  float4 *vc = reinterpret_cast<float4 *>(tb2 + NT);          // [NT] backward coefficients
-  float *red1 = reinterpret_cast<float *>(vc + NT), *red2 = red1 + 16 * NH;   // [16][NH] each
-  float *zbuf = red2 + 16 * NH, *wbuf = zbuf + 512;           // [2][256] each
+  float *viy = tb2 + NT, *vY = viy + 2 * NT;                  // [2][NT] each: 1/Y (backward), Y (forward)
+  float4 *vc = reinterpret_cast<float4 *>(vY + 2 * NT);       // [2][NT] backward coefficients
+  float *red1 = reinterpret_cast<float *>(vc + 2 * NT), *red2 = red1 + 32 * NH;   // [2][16][NH] each
+  float *zbuf = red2 + 32 * NH, *wbuf = zbuf + 512;           // [2][256] each
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = (BWD ? p.i0 : 0) + blockIdx.x;
@@ -193,11 +219,11 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     vu[t] = in ? p.unorm[(int64_t)i * T + t] : 1.f;
     tb[t] = (in && p.mask[(int64_t)i * T + t]) ? 0.f : -INFINITY;
     tb2[t] = in ? 0.f : -INFINITY;
-    vc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    viy[t] = 0.f;
+    vc[t] = vc[NT + t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    viy[t] = viy[NT + t] = 0.f;
   }
-  if (warp == 17) tmem_alloc<512>(tmem_ptr);
-  if (warp == 16 && lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmV); prefetch_tmap(&tmG); }
+  if (warp == MMA_WARP) tmem_alloc<512>(tmem_ptr);
+  if (warp == TMA_WARP && lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmV); prefetch_tmap(&tmG); }
   fence_proxy_async_smem();           // the zero fill must be ordered before the TMA / MMA (async proxy) accesses
   tc_fence_before();
   __syncthreads();
@@ -206,7 +232,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t idesc = umma_idesc_f16(NT);
   const uint32_t col_m = (uint32_t)(nbuf * L.tiles * NT);     // TMEM column of M'
 
-  if (warp == 16) {
+  if (warp == TMA_WARP) {
     // ===================================== TMA producer =====================================
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, L.q_bytes);
@@ -231,7 +257,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int j = j0; j < j1; ++j) { load(&tmV, L.nkb_d, j); load(&tmG, L.nkb_r, j); }
       }
     }
-  } else if (warp == 17) {
+  } else if (warp == MMA_WARP) {
     // ===================================== MMA issuer =====================================
     if (elect_one()) {
       mbar_wait(q_full, 0);
@@ -306,15 +332,60 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     const float4 *tb4 = reinterpret_cast<const float4 *>(tb + c0);
     const float2 *tb22 = reinterpret_cast<const float2 *>(tb2 + c0);
-    const float4 *vch = vc + c0;
-    float *red1w = red1 + warp * NH, *red2w = red2 + warp * NH;
+    float *red1w0 = red1 + warp * NH, *red2w0 = red2 + warp * NH;
     const int widx = (warp & 7) * 32 + lane;                        // row slot in zbuf / wbuf
-    const int sidx = (half * (L.act_warps / 2) + (warp & 7)) * 32 + lane;   // rank among the active softmax threads
+    constexpr int CPL = (NT + 31) / 32;                             // words per lane in the one-warp sections
+    // backward, warp 0: per-row constants of dL/dsim (both cross-entropies, losses.py:265-269)
+    float bw_rl = 0.f, bw_g0 = 0.f, bw_g1 = 0.f, bw_ib = 0.f;
+    int64_t bw_gi = 0, bw_li = 0;
+    if (BWD && warp == 0) {
+      bw_gi = p.row_offset + i;
+      bw_li = p.labels ? p.labels[bw_gi] : bw_gi;
+      bw_rl = p.row_lse[i];
+      bw_g0 = p.gscale[0]; bw_g1 = p.gscale[1];
+      bw_ib = 1.f / (float)p.b_total;
+    }
     for (int j = j0, it = 0; j < j1; ++j, ++it) {
       const int b = it % nbuf;
       const uint32_t t_s = t_lane + (uint32_t)(b * L.tiles * NT);
       float e1[NH];
       uint32_t e2p[NH / 2];
+      const int rb = it & 1;                                        // parity of the double-buffered bookkeeping
+      float *red1w = red1w0 + rb * 16 * NH, *red2w = red2w0 + rb * 16 * NH;
+      float *vYb = vY + rb * NT;
+      float4 *vcb = vc + rb * NT;
+      float *viyb = viy + rb * NT;
+      if constexpr (BWD) {
+        // ---- warp 0: per-word coefficients from the statistics the forward saved (rho, ||c||, 1/Y):
+        //      beta = dL/drho, a = beta/(n u), b = beta rho / n^2.  Overlaps the wait for GEMM1.
+        if (warp == 0) {
+          const int64_t pair = (int64_t)i * p.bc + j;
+          const float sv = p.sim[pair];
+          float g = 0.f;
+          if (sv != -INFINITY) {                                    // exactly 0 where class-masked
+            const int64_t lj = p.labels ? p.labels[j] : (int64_t)j;
+            const float gr = __expf(sv - bw_rl) - (bw_li == j ? 1.f : 0.f);
+            const float gc = __expf(sv - p.col_lse[j]) - (lj == bw_gi ? 1.f : 0.f);
+            g = (bw_g0 * gr + bw_g1 * gc) * bw_ib;
+          }
+          const float lse = (sv != -INFINITY) ? sv * (p.g2 / p.g3) : 0.f;   // sim = gamma3/gamma2 * lse
+          const float *st = p.stats + pair * 3 * T;
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+            const int t = q * 32 + lane;
+            if (t < T) {
+              const float rho = st[t], n = st[T + t], iy = st[2 * T + t];
+              const float omega = __expf(p.g2 * rho - lse);
+              const float beta = g * p.g3 * omega;                  // dL/drho_t
+              const float a = beta / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
+              const float bq = (n > kCosEps) ? beta * rho / (n * n) : 0.f;
+              vcb[t] = make_float4(p.g1 * a * iy, p.g1 * bq * iy * iy, a * iy * p.scale_ds, bq * iy * p.scale_ba);
+              viyb[t] = iy;
+              atomicAdd(p.kq + (int64_t)i * T + t, beta * rho);
+            }
+          }
+        }
+      }
       mbar_wait(&s_full[b], (it / nbuf) & 1);
       tc_fence_after();
       // ---- pass A: e1 = exp(S + mask bias), Z = sum_t e1 (softmax over words, losses.py:127,143-144) ----
@@ -333,16 +404,17 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       zbuf[half * 256 + widx] = zp;
-      named_bar_sync(1, nsoft);
+      named_bar_sync(1, nsoft);                                     // also publishes warp 0's coefficients (backward)
       const float Z = zbuf[widx] + zbuf[256 + widx];
       const float invZ = 1.f / Z;
       const float k2 = p.g1 * kLog2e * invZ;
-      // ---- pass B: e2 = exp(gamma1 P) (softmax over regions, un-normalised) -> fp16 B operand; N' partials ----
+      // ---- pass B: e2 = exp(gamma1 P) (softmax over regions, un-normalised) -> fp16 B operand of GEMM2;
+      //      forward also forms the N' = sum_r e2 S partial sums ----
       auto pass_b = [&](auto width, auto cb) {
         constexpr int W = decltype(width)::value;
         constexpr int cbeg = decltype(cb)::value;
         float x[W];
-        tmem_ld<W>(t_s + cbeg, x);
+        if constexpr (!BWD) tmem_ld<W>(t_s + cbeg, x);
 #pragma unroll
         for (int k = 0; k < W; k += 2) {
           const int tl = cbeg + k;
@@ -355,12 +427,16 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             sts_u16(e2a[tl & 7] + tl * 128, h2 & 0xffffu);
             sts_u16(e2a[(tl + 1) & 7] + (tl + 1) * 128, h2 >> 16);
           }
-          const float2 f = unpack_half2(h2);                        // the values the tensor core will see
-          x[k] *= f.x;
-          x[k + 1] *= f.y;
+          if constexpr (!BWD) {
+            const float2 f = unpack_half2(h2);                      // the values the tensor core will see
+            x[k] *= f.x;
+            x[k + 1] *= f.y;
+          }
         }
-        const float cs = warp_colsum<W>(x, lane);
-        if (lane < W) red1w[cbeg + lane] = cs;
+        if constexpr (!BWD) {
+          const float cs = warp_colsum<W>(x, lane);
+          if (lane < W) red1w[cbeg + lane] = cs;
+        }
       };
       if constexpr (NH >= 32) pass_b(std::integral_constant<int, 32>{}, std::integral_constant<int, 0>{});
       if constexpr (NH == 64) pass_b(std::integral_constant<int, 32>{}, std::integral_constant<int, 32>{});
@@ -370,96 +446,80 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       mbar_arrive(e2_ready);
       if (!BWD) mbar_arrive(&s_free[b]);                            // forward: S is dead from here on
-      // ---- after GEMM2: NN partial sums; the appended ones-row delivers Y_t ----
       mbar_wait(m_full, it & 1);
       tc_fence_after();
-      auto pass_m = [&](auto width, auto cb) {
-        constexpr int W = decltype(width)::value;
-        constexpr int cbeg = decltype(cb)::value;
-        float x[W];
-        tmem_ld<W>(t_m + cbeg, x);
-        if (rg == R) {
+      if constexpr (!BWD) {
+        // ---- NN = sum_r e2 M' partial sums; the appended ones-row delivers Y_t ----
+        auto pass_m = [&](auto width, auto cb) {
+          constexpr int W = decltype(width)::value;
+          constexpr int cbeg = decltype(cb)::value;
+          float x[W];
+          tmem_ld<W>(t_m + cbeg, x);
+          if (rg == R) {
 #pragma unroll
-          for (int k = 0; k < W; ++k) vY[c0 + cbeg + k] = x[k];
-        }
-#pragma unroll
-        for (int k = 0; k < W; k += 2) {
-          const float2 f = unpack_half2(e2p[(cbeg + k) >> 1]);
-          x[k] *= f.x;
-          x[k + 1] *= f.y;
-        }
-        const float cs = warp_colsum<W>(x, lane);
-        if (lane < W) red2w[cbeg + lane] = cs;
-      };
-      if constexpr (NH >= 32) pass_m(std::integral_constant<int, 32>{}, std::integral_constant<int, 0>{});
-      if constexpr (NH == 64) pass_m(std::integral_constant<int, 32>{}, std::integral_constant<int, 32>{});
-      if constexpr (NH == 40) pass_m(std::integral_constant<int, 8>{}, std::integral_constant<int, 32>{});
-      if constexpr (NH == 16) pass_m(std::integral_constant<int, 16>{}, std::integral_constant<int, 0>{});
-      if (!BWD) { tc_fence_before(); mbar_arrive(m_free); }
-      named_bar_sync(1, nsoft);
-      // ---- per-word cosine (losses.py:197-198) and gamma2 log-sum-exp (:199-203) ----
-      for (int t = sidx; t < T; t += nsoft) {
-        const int h = t / NH, tl = t - h * NH;
-        float np = 0.f, nn = 0.f;
-        for (int w = 0; w < L.act_warps / 2; ++w) {
-          np += red1[(h * 8 + w) * NH + tl];
-          nn += red2[(h * 8 + w) * NH + tl];
-        }
-        const float y = vY[t];
-        const float n = sqrtf(fmaxf(nn, 0.f)) / y;
-        const float rho = (np / y) / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
-        vxs[t] = p.g2 * rho;
-        if (BWD) { vrho[t] = rho; vn[t] = n; viy[t] = 1.f / y; }
-      }
-      named_bar_sync(1, nsoft);
-      if (warp == 0) {
-        float mx = -INFINITY;
-        for (int t = lane; t < T; t += 32) mx = fmaxf(mx, vxs[t]);
-        mx = warp_max(mx);
-        float se = 0.f;
-        for (int t = lane; t < T; t += 32) se += __expf(vxs[t] - mx);
-        se = warp_sum(se);
-        if (lane == 0) {
-          if (!BWD) {
-            p.sim[(int64_t)i * p.bc + j] = p.g3 * ((__logf(se) + mx) / p.g2);
-          } else {
-            // dL/dsim for this pair from both cross-entropies (losses.py:265-269); exactly 0 where class-masked
-            const float s = p.sim[(int64_t)i * p.bc + j];
-            float g = 0.f;
-            if (s != -INFINITY) {
-              const int64_t gi = p.row_offset + i;
-              const int64_t li = p.labels ? p.labels[gi] : gi;
-              const int64_t lj = p.labels ? p.labels[j] : (int64_t)j;
-              const float gr = __expf(s - p.row_lse[i]) - (li == j ? 1.f : 0.f);
-              const float gc = __expf(s - p.col_lse[j]) - (lj == gi ? 1.f : 0.f);
-              g = (p.gscale[0] * gr + p.gscale[1] * gc) / (float)p.b_total;
-            }
-            vmisc[0] = __logf(se) + mx;
-            vmisc[1] = g;
+            for (int k = 0; k < W; ++k) vYb[c0 + cbeg + k] = x[k];
           }
-        }
-      }
-      // The next pair's zbuf barrier orders this pair's reads of red1/red2/vxs/vY before they are rewritten.
-      if (BWD) {
+#pragma unroll
+          for (int k = 0; k < W; k += 2) {
+            const float2 f = unpack_half2(e2p[(cbeg + k) >> 1]);
+            x[k] *= f.x;
+            x[k + 1] *= f.y;
+          }
+          const float cs = warp_colsum<W>(x, lane);
+          if (lane < W) red2w[cbeg + lane] = cs;
+        };
+        if constexpr (NH >= 32) pass_m(std::integral_constant<int, 32>{}, std::integral_constant<int, 0>{});
+        if constexpr (NH == 64) pass_m(std::integral_constant<int, 32>{}, std::integral_constant<int, 32>{});
+        if constexpr (NH == 40) pass_m(std::integral_constant<int, 8>{}, std::integral_constant<int, 32>{});
+        if constexpr (NH == 16) pass_m(std::integral_constant<int, 16>{}, std::integral_constant<int, 0>{});
+        tc_fence_before();
+        mbar_arrive(m_free);
         named_bar_sync(1, nsoft);
-        // ---- per-word backward coefficients: beta = dL/drho, a = beta/(n u), b = beta rho / n^2 ----
-        for (int t = sidx; t < T; t += nsoft) {
-          const float omega = __expf(vxs[t] - vmisc[0]);
-          const float beta = vmisc[1] * p.g3 * omega;
-          const float n = vn[t], rho = vrho[t], iy = viy[t];
-          const float a = beta / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
-          const float bq = (n > kCosEps) ? beta * rho / (n * n) : 0.f;
-          vc[t] = make_float4(p.g1 * a * iy, p.g1 * bq * iy * iy, a * iy * p.scale_ds, bq * iy * p.scale_ba);
-          atomicAdd(p.kq + (int64_t)i * T + t, beta * rho);
+        // ---- serial tail, one warp, nobody waits for it (bookkeeping is double-buffered by pair parity):
+        //      per-word cosine (losses.py:197-198), gamma2 log-sum-exp (:199-203), statistics for the backward ----
+        if (warp == 0) {
+          const float *r1 = red1 + rb * 16 * NH, *r2 = red2 + rb * 16 * NH;
+          const int64_t pair = (int64_t)i * p.bc + j;
+          float *st = p.stats ? p.stats + pair * 3 * T : nullptr;
+          float xv[CPL];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+            const int t = q * 32 + lane;
+            xv[q] = -INFINITY;
+            if (t < T) {
+              const int h = t / NH, tl = t - h * NH;
+              float np = 0.f, nn = 0.f;
+              for (int w = 0; w < L.act_warps / 2; ++w) {
+                np += r1[(h * 8 + w) * NH + tl];
+                nn += r2[(h * 8 + w) * NH + tl];
+              }
+              const float iy = 1.f / vYb[t];
+              const float n = sqrtf(fmaxf(nn, 0.f)) * iy;
+              const float rho = (np * iy) / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
+              if (st) { st[t] = rho; st[T + t] = n; st[2 * T + t] = iy; }
+              xv[q] = p.g2 * rho;
+              mx = fmaxf(mx, xv[q]);
+            }
+          }
+          mx = warp_max(mx);
+          float se = 0.f;
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) se += __expf(xv[q] - mx);   // exp(-inf) = 0 for the unused slots
+          se = warp_sum(se);
+          if (lane == 0) p.sim[pair] = p.g3 * ((__logf(se) + mx) / p.g2);
         }
-        named_bar_sync(1, nsoft);
+      } else {
+        const float4 *vch = vcb + c0;
+        const float *viyh = viyb + c0;
         // ---- W = sum_t P dP with dP = gamma1 A (a S - b M)  (this row, all words: two halves via wbuf) ----
         float wp = 0.f;
 #pragma unroll
         for (int c = 0; c < NH / 8; ++c) {
           float xs[8], xm[8];
-          tmem_ld<8>(t_s + c * 8, xs);
-          tmem_ld<8>(t_m + c * 8, xm);
+          tmem_ld8_issue(t_s + c * 8, xs);
+          tmem_ld8_issue(t_m + c * 8, xm);
+          tmem_wait16(xs, xm);
 #pragma unroll
           for (int k = 0; k < 8; k += 2) {
             const int tl = c * 8 + k;
@@ -484,8 +544,9 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int c = 0; c < NH / 8; ++c) {
             if (c0 + c * 8 < p.tp) {                                 // warp-uniform: tcgen05.ld is warp-collective
               float xs[8], xm[8];
-              tmem_ld<8>(t_s + c * 8, xs);
-              tmem_ld<8>(t_m + c * 8, xm);
+              tmem_ld8_issue(t_s + c * 8, xs);
+              tmem_ld8_issue(t_m + c * 8, xm);
+              tmem_wait16(xs, xm);
               uint32_t pk_ds[4], pk_a[4], pk_ba[4];
 #pragma unroll
               for (int k = 0; k < 8; k += 2) {
@@ -494,16 +555,11 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const float4 ca = vch[tl], cb = vch[tl + 1];
                 const float dp0 = f.x * (ca.x * xs[k] - ca.y * xm[k]);
                 const float dp1 = f.y * (cb.x * xs[k + 1] - cb.y * xm[k + 1]);
-                float ds0 = fmaf(ca.z, f.x, sp * e1[tl] * (dp0 - Wr));
-                float ds1 = fmaf(cb.z, f.y, sp * e1[tl + 1] * (dp1 - Wr));
-                float ba0 = ca.w * f.x, ba1 = cb.w * f.y;
-                ds0 = fminf(fmaxf(ds0, -65504.f), 65504.f);
-                ds1 = fminf(fmaxf(ds1, -65504.f), 65504.f);
-                ba0 = fminf(fmaxf(ba0, -65504.f), 65504.f);
-                ba1 = fminf(fmaxf(ba1, -65504.f), 65504.f);
-                pk_ds[k >> 1] = pack_half2(ds0, ds1);
-                pk_a[k >> 1] = pack_half2(viy[c0 + tl] * f.x, viy[c0 + tl + 1] * f.y);
-                pk_ba[k >> 1] = pack_half2(ba0, ba1);
+                const float ds0 = fmaf(ca.z, f.x, sp * e1[tl] * (dp0 - Wr));
+                const float ds1 = fmaf(cb.z, f.y, sp * e1[tl + 1] * (dp1 - Wr));
+                pk_ds[k >> 1] = pack_half2_sat(ds0, ds1);
+                pk_a[k >> 1] = pack_half2(viyh[tl] * f.x, viyh[tl + 1] * f.y);
+                pk_ba[k >> 1] = pack_half2_sat(ca.w * f.x, cb.w * f.y);
               }
               if (valid) {
                 o_ds[c] = make_uint4(pk_ds[0], pk_ds[1], pk_ds[2], pk_ds[3]);
@@ -521,7 +577,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 17) tmem_dealloc<512>(tmem_base);
+  if (warp == MMA_WARP) tmem_dealloc<512>(tmem_base);
 }
 
 // ----------------------------------------------------------------------------------------------- host side
@@ -620,9 +676,15 @@ static int tc_launch(const TcLaunch &tl, TcParams &p, int64_t rows, cudaStream_t
   dim3 grid((unsigned)rows, (unsigned)splits);
 #define DAMSM_LAUNCH_TC(NT_)                                                                                          \
   do {                                                                                                                \
-    DAMSM_CUDA(cudaFuncSetAttribute(words_tc_kernel<NT_, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
-                                    (int)tl.L.total));                                                                \
-    words_tc_kernel<NT_, BWD><<<grid, TC_THREADS, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, p);                       \
+    if (tl.L.act_warps <= 14) {                                                                                       \
+      DAMSM_CUDA(cudaFuncSetAttribute(words_tc_kernel<NT_, BWD, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                      (int)tl.L.total));                                                              \
+      words_tc_kernel<NT_, BWD, 16><<<grid, 16 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, p);                    \
+    } else {                                                                                                          \
+      DAMSM_CUDA(cudaFuncSetAttribute(words_tc_kernel<NT_, BWD, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                      (int)tl.L.total));                                                              \
+      words_tc_kernel<NT_, BWD, 18><<<grid, 18 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, p);                    \
+    }                                                                                                                 \
   } while (0)
   switch (tl.nt) {
     case 32: DAMSM_LAUNCH_TC(32); break;
@@ -670,7 +732,8 @@ extern "C" int64_t damsm_words_tc_smem_bytes(int64_t t, int64_t r, int64_t d) {
 
 extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
                                   const float *unorm, const uint8_t *mask, int64_t br, int64_t bc, int64_t t, int64_t r,
-                                  int64_t d, float gamma1, float gamma2, float gamma3, float *sim, void *stream) {
+                                  int64_t d, float gamma1, float gamma2, float gamma3, float *sim, float *stats,
+                                  void *stream) {
   DAMSM_REQUIRE(qhat16 && vhat16 && gx && unorm && mask && sim, "words_fwd_tc: null pointer");
   if (br == 0 || bc == 0) return 0;
   TcLaunch tl;
@@ -678,7 +741,7 @@ extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void
   if ((rc = tc_prepare(&tl, "words_fwd_tc", qhat16, q_rows, vhat16, gx, br, bc, t, r, d))) return rc;
   TcParams p{};
   p.br = (int)br; p.bc = (int)bc; p.T = (int)t; p.R = (int)r; p.D = (int)d;
-  p.g1 = gamma1; p.g2 = gamma2; p.g3 = gamma3; p.mask = mask; p.unorm = unorm; p.sim = sim;
+  p.g1 = gamma1; p.g2 = gamma2; p.g3 = gamma3; p.mask = mask; p.unorm = unorm; p.sim = sim; p.stats = stats;
   return tc_launch<false>(tl, p, br, (cudaStream_t)stream);
 }
 
@@ -689,13 +752,14 @@ extern "C" int64_t damsm_words_bwd_tc_row_bytes(int64_t bc, int64_t t, int64_t r
 }
 
 extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
-                                  const float *unorm, const uint8_t *mask, const float *sim, const float *row_lse,
-                                  const float *col_lse, const int64_t *labels, const float *gscale, int64_t row_offset,
+                                  const float *unorm, const uint8_t *mask, const float *sim, const float *stats,
+                                  const float *row_lse, const float *col_lse, const int64_t *labels,
+                                  const float *gscale, int64_t row_offset,
                                   int64_t b_total, int64_t br, int64_t bc, int64_t t, int64_t r, int64_t d, float gamma1,
                                   float gamma2, float gamma3, void *workspace, int64_t workspace_bytes, float *dqhat,
                                   float *dvhat, float *hmat, float *kq, void *stream) {
-  DAMSM_REQUIRE(qhat16 && vhat16 && gx && unorm && mask && sim && row_lse && col_lse && gscale && workspace && dqhat &&
-                    dvhat && hmat && kq, "words_bwd_tc: null pointer");
+  DAMSM_REQUIRE(qhat16 && vhat16 && gx && unorm && mask && sim && stats && row_lse && col_lse && gscale && workspace &&
+                    dqhat && dvhat && hmat && kq, "words_bwd_tc: null pointer");
   const int64_t tp = (t + 7) / 8 * 8;
   DAMSM_REQUIRE(q_rows == tp, "words_bwd_tc: qhat16 must be padded to %lld rows per caption (got %lld)", (long long)tp,
                 (long long)q_rows);
@@ -729,6 +793,7 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
     TcParams p{};
     p.br = (int)br; p.bc = (int)bc; p.T = (int)t; p.R = (int)r; p.D = (int)d;
     p.g1 = gamma1; p.g2 = gamma2; p.g3 = gamma3; p.mask = mask; p.unorm = unorm; p.sim = const_cast<float *>(sim);
+    p.stats = const_cast<float *>(stats);
     p.i0 = (int)i0; p.tp = (int)tp; p.kc = kc; p.row_lse = row_lse; p.col_lse = col_lse; p.gscale = gscale;
     p.labels = labels; p.row_offset = row_offset; p.b_total = b_total; p.kq = kq;
     p.x_ds = x_ds; p.x_a = x_a; p.x_ba = x_ba; p.scale_ds = scale_ds; p.scale_ba = scale_ba;

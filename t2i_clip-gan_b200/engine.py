@@ -89,16 +89,20 @@ class CudaEngine:
             col["vhat16"] = vhat16
         return col
 
-    def words_fwd(self, qhat, qhat16, vhat, col, unorm, mask_u8, gammas):
+    def words_fwd(self, qhat, qhat16, vhat, col, unorm, mask_u8, gammas, want_stats=True):
         _require_cuda(qhat, vhat, unorm, mask_u8)
         br, t, d = qhat.shape
         bc, r, _ = vhat.shape
         sim = torch.empty((br, bc), device=qhat.device, dtype=torch.float32)
         if self.precision == "bf16":
+            # per-pair, per-word scalars (rho, ||c||, 1/Y) for the backward: 12*T bytes per pair
+            stats = torch.empty((br, bc, 3, t), device=qhat.device, dtype=torch.float32) if want_stats else None
+            col["stats"] = stats
             _lib.call("damsm_words_fwd_tc", qhat16.data_ptr(), qhat16.shape[1], col["vhat16"].data_ptr(),
                       col["gx"].data_ptr(),
                       unorm.data_ptr(), mask_u8.data_ptr(), br, bc, t, r, d,
-                      float(gammas[0]), float(gammas[1]), float(gammas[2]), sim.data_ptr(), _stream())
+                      float(gammas[0]), float(gammas[1]), float(gammas[2]), sim.data_ptr(), _lib.ptr(stats),
+                      _stream())
         else:
             _lib.call("damsm_words_fwd_f32", qhat.data_ptr(), vhat.data_ptr(), col["gram"].data_ptr(),
                       unorm.data_ptr(), mask_u8.data_ptr(), br, bc, t, r, d,
@@ -143,7 +147,8 @@ class CudaEngine:
         hmat = torch.zeros((bc, r, r), device=dev, dtype=torch.float32)
         kq = torch.zeros((br, t), device=dev, dtype=torch.float32)
         _lib.call("damsm_words_bwd_tc", qhat16.data_ptr(), tp, col["vhat16"].data_ptr(), col["gx"].data_ptr(),
-                  unorm.data_ptr(), mask_u8.data_ptr(), sim.data_ptr(), row_lse.data_ptr(), col_lse.data_ptr(),
+                  unorm.data_ptr(), mask_u8.data_ptr(), sim.data_ptr(), col["stats"].data_ptr(),
+                  row_lse.data_ptr(), col_lse.data_ptr(),
                   _lib.ptr(labels), gscale.data_ptr(), int(row_offset), int(b_total), br, bc, t, r, d,
                   float(gammas[0]), float(gammas[1]), float(gammas[2]), ws.data_ptr(), ws_bytes,
                   dqhat.data_ptr(), dvhat.data_ptr(), hmat.data_ptr(), kq.data_ptr(), _stream())
