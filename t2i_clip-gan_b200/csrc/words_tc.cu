@@ -59,9 +59,17 @@ __host__ __device__ inline TcLayout tc_layout(int NT, int R, int D) {
   l.misc_off = l.q_bytes + TC_STAGES * l.stage_bytes + l.e2_bytes;
   // misc: 256 B of barriers / scalars, then floats: u,tb,tb2 [NT] + iy,Y [2][NT] + vc float4 [2][NT] +
   // red1/red2 [2][16][NT/2] + zbuf/wbuf [2][256]   ([2] = double-buffered by pair parity)
-  l.total = l.misc_off + 256 + 4 * (7 * NT + 8 * NT + 32 * NT + 1024) + 1024 /*alignment slack*/;
+  l.total = l.misc_off + 256 + 4 * (7 * NT + 8 * NT + 32 * NT + 2048) + 1024 /*alignment slack*/;
   return l;
 }
+
+// Development switches for timing experiments (compile with -DDAMSM_TC_DEBUG and set env DAMSM_DBG):
+// 1 no scratch stores, 2 no sweep 2, 4 no sweeps, 8/16 skip Gx / vhat TMA loads, 32 no softmax math, 64 no MMAs.
+#ifdef DAMSM_TC_DEBUG
+#define DBG(p, bit) ((p).dbg & (bit))
+#else
+#define DBG(p, bit) (0)
+#endif
 
 struct TcParams {
   int br, bc, T, R, D;
@@ -81,6 +89,7 @@ struct TcParams {
   float *kq;
   __half *x_ds, *x_a, *x_ba;          // scratch matrices [(j, r)][(i_local, t)], fp16
   float scale_ds, scale_ba;           // power-of-two scales that keep dS and diag(b)A in fp16's normal range
+  int dbg;                            // development switches (env DAMSM_DBG): 1 no stores, 2 no sweep 2, 4 no sweeps
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -187,6 +196,8 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t *s_full = q_full + 1;                      // 7,8   (one per S buffer)
   uint64_t *s_free = q_full + 3;                      // 9,10
   uint64_t *e2_ready = q_full + 5, *m_full = q_full + 6, *m_free = q_full + 7;   // 11,12,13
+  uint64_t *red_full = q_full + 8;                                               // 14 (forward: reductions published)
+  uint64_t *coef_full = q_full + 9;                                              // 15 (backward: coefficients published)
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 16);
   float *vu = reinterpret_cast<float *>(misc + 256);          // [NT] ||qhat_t||
   float *tb = vu + NT;                                        // 0 for real words, -inf for padding and t >= T
@@ -194,7 +205,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float *viy = tb2 + NT, *vY = viy + 2 * NT;                  // [2][NT] each: 1/Y (backward), Y (forward)
   float4 *vc = reinterpret_cast<float4 *>(vY + 2 * NT);       // [2][NT] backward coefficients
   float *red1 = reinterpret_cast<float *>(vc + 2 * NT), *red2 = red1 + 32 * NH;   // [2][16][NH] each
-  float *zbuf = red2 + 32 * NH, *wbuf = zbuf + 512;           // [2][256] each
+  float *zbuf = red2 + 32 * NH, *wbuf = zbuf + 1024;          // [2 parities][2 halves][256] each
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = (BWD ? p.i0 : 0) + blockIdx.x;
@@ -211,7 +222,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(q_full, 1); mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(m_full, 1);
     mbar_init(&s_free[0], nsoft); mbar_init(&s_free[1], nsoft);
-    mbar_init(e2_ready, nsoft); mbar_init(m_free, nsoft);
+    mbar_init(e2_ready, nsoft); mbar_init(m_free, nsoft); mbar_init(red_full, nsoft); mbar_init(coef_full, 1);
     fence_barrier_init();
   }
   for (int t = threadIdx.x; t < NT; t += TC_THREADS) {
@@ -241,8 +252,12 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       auto load = [&](const CUtensorMap *m, int nkb, int j) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
+          if (DBG(p, 8) && m == &tmG) { mbar_arrive(&full[stage]); }          // timing experiments only
+          else if (DBG(p, 16) && m == &tmV) { mbar_arrive(&full[stage]); }
+          else {
           mbar_arrive_expect_tx(&full[stage], (uint32_t)L.rs * 128);
           tma_load_3d(stages + stage * L.stage_bytes, m, &full[stage], kb * 64, 0, j);
+          }
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
       };
@@ -274,6 +289,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             for (int tl = 0; tl < L.tiles; ++tl)
+              if (!DBG(p, 64))
               umma_f16(d0 + tl * NT, umma_desc_k_sw128(a0 + tl * 16384 + k * 32), umma_desc_k_sw128(b0 + k * 32),
                        idesc, (kb | k) != 0);
           umma_commit(&empty[stage]);
@@ -293,6 +309,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const int nk = min(4, left);
           for (int k = 0; k < nk; ++k)
             for (int tl = 0; tl < L.tiles; ++tl)
+              if (!DBG(p, 64))
               umma_f16(tmem_base + col_m + tl * NT, umma_desc_k_sw128(a0 + tl * 16384 + k * 32),
                        umma_desc_k_sw128(b0 + k * 32), idesc, (kb | k) != 0);
           left -= nk;
@@ -355,41 +372,16 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float *vYb = vY + rb * NT;
       float4 *vcb = vc + rb * NT;
       float *viyb = viy + rb * NT;
-      if constexpr (BWD) {
-        // ---- warp 0: per-word coefficients from the statistics the forward saved (rho, ||c||, 1/Y):
-        //      beta = dL/drho, a = beta/(n u), b = beta rho / n^2.  Overlaps the wait for GEMM1.
-        if (warp == 0) {
-          const int64_t pair = (int64_t)i * p.bc + j;
-          const float sv = p.sim[pair];
-          float g = 0.f;
-          if (sv != -INFINITY) {                                    // exactly 0 where class-masked
-            const int64_t lj = p.labels ? p.labels[j] : (int64_t)j;
-            const float gr = __expf(sv - bw_rl) - (bw_li == j ? 1.f : 0.f);
-            const float gc = __expf(sv - p.col_lse[j]) - (lj == bw_gi ? 1.f : 0.f);
-            g = (bw_g0 * gr + bw_g1 * gc) * bw_ib;
-          }
-          const float lse = (sv != -INFINITY) ? sv * (p.g2 / p.g3) : 0.f;   // sim = gamma3/gamma2 * lse
-          const float *st = p.stats + pair * 3 * T;
-#pragma unroll
-          for (int q = 0; q < CPL; ++q) {
-            const int t = q * 32 + lane;
-            if (t < T) {
-              const float rho = st[t], n = st[T + t], iy = st[2 * T + t];
-              const float omega = __expf(p.g2 * rho - lse);
-              const float beta = g * p.g3 * omega;                  // dL/drho_t
-              const float a = beta / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
-              const float bq = (n > kCosEps) ? beta * rho / (n * n) : 0.f;
-              vcb[t] = make_float4(p.g1 * a * iy, p.g1 * bq * iy * iy, a * iy * p.scale_ds, bq * iy * p.scale_ba);
-              viyb[t] = iy;
-              atomicAdd(p.kq + (int64_t)i * T + t, beta * rho);
-            }
-          }
-        }
-      }
       mbar_wait(&s_full[b], (it / nbuf) & 1);
       tc_fence_after();
       // ---- pass A: e1 = exp(S + mask bias), Z = sum_t e1 (softmax over words, losses.py:127,143-144) ----
       float zp = 0.f;
+      if (DBG(p, 32)) {
+#pragma unroll
+        for (int c = 0; c < NH; ++c) e1[c] = 1.f;
+#pragma unroll
+        for (int c = 0; c < NH / 2; ++c) e2p[c] = 0;
+      } else
 #pragma unroll
       for (int c = 0; c < NH / 8; ++c) {
         float x[8];
@@ -403,9 +395,11 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           zp += e;
         }
       }
-      zbuf[half * 256 + widx] = zp;
-      named_bar_sync(1, nsoft);                                     // also publishes warp 0's coefficients (backward)
-      const float Z = zbuf[widx] + zbuf[256 + widx];
+      float *zb = zbuf + rb * 512, *wb = wbuf + rb * 512;
+      zb[half * 256 + widx] = zp;
+      // only the two warps that share these rows (word halves) exchange Z: a 64-thread named barrier per pair
+      named_bar_sync(2 + (warp & 7), 64);
+      const float Z = zb[widx] + zb[256 + widx];
       const float invZ = 1.f / Z;
       const float k2 = p.g1 * kLog2e * invZ;
       // ---- pass B: e2 = exp(gamma1 P) (softmax over regions, un-normalised) -> fp16 B operand of GEMM2;
@@ -438,15 +432,60 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (lane < W) red1w[cbeg + lane] = cs;
         }
       };
+      if (!DBG(p, 32)) {
       if constexpr (NH >= 32) pass_b(std::integral_constant<int, 32>{}, std::integral_constant<int, 0>{});
       if constexpr (NH == 64) pass_b(std::integral_constant<int, 32>{}, std::integral_constant<int, 32>{});
       if constexpr (NH == 40) pass_b(std::integral_constant<int, 8>{}, std::integral_constant<int, 32>{});
       if constexpr (NH == 16) pass_b(std::integral_constant<int, 16>{}, std::integral_constant<int, 0>{});
+      }
+      // backward: the sweeps only need P = e1/Z to fp16 accuracy; halving its registers keeps them spill-free
+      // (spills go to L2 here: the L1 is almost entirely carved out as shared memory)
+      uint32_t e1h[BWD ? NH / 2 : 1];
+      if constexpr (BWD) {
+#pragma unroll
+        for (int k = 0; k < NH / 2; ++k) e1h[k] = pack_half2(e1[2 * k] * invZ, e1[2 * k + 1] * invZ);
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(e2_ready);
       if (!BWD) mbar_arrive(&s_free[b]);                            // forward: S is dead from here on
+      if constexpr (BWD) {
+        // ---- warp 0: per-word coefficients from the statistics the forward saved (rho, ||c||, 1/Y):
+        //      beta = dL/drho, a = beta/(n u), b = beta rho / n^2.  Runs while GEMM2 is in flight; the sweeps of every
+        //      warp read it after m_full, which GEMM2 signals only after this warp... (published by coef_full).
+        if (warp == 0) {
+          const int64_t pair = (int64_t)i * p.bc + j;
+          const float sv = p.sim[pair];
+          float g = 0.f;
+          if (sv != -INFINITY) {                                    // exactly 0 where class-masked
+            const int64_t lj = p.labels ? p.labels[j] : (int64_t)j;
+            const float gr = __expf(sv - bw_rl) - (bw_li == j ? 1.f : 0.f);
+            const float gc = __expf(sv - p.col_lse[j]) - (lj == bw_gi ? 1.f : 0.f);
+            g = (bw_g0 * gr + bw_g1 * gc) * bw_ib;
+          }
+          const float lse = (sv != -INFINITY) ? sv * (p.g2 / p.g3) : 0.f;   // sim = gamma3/gamma2 * lse
+          const float *st = p.stats + pair * 3 * T;
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+            const int t = q * 32 + lane;
+            if (t < T) {
+              const float rho = st[t], n = st[T + t], iy = st[2 * T + t];
+              const float omega = __expf(p.g2 * rho - lse);
+              const float beta = g * p.g3 * omega;                  // dL/drho_t
+              const float a = beta / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
+              const float bq = (n > kCosEps) ? beta * rho / (n * n) : 0.f;
+              vcb[t] = make_float4(p.g1 * a * iy, p.g1 * bq * iy * iy, a * iy * p.scale_ds, bq * iy * p.scale_ba);
+              viyb[t] = iy;
+              atomicAdd(p.kq + (int64_t)i * T + t, beta * rho);
+            }
+          }
+        }
+      }
+      if constexpr (BWD) {
+        if (warp == 0) { __syncwarp(); if (lane == 0) mbar_arrive(coef_full); }
+      }
       mbar_wait(m_full, it & 1);
+      if constexpr (BWD) mbar_wait(coef_full, it & 1);
       tc_fence_after();
       if constexpr (!BWD) {
         // ---- NN = sum_r e2 M' partial sums; the appended ones-row delivers Y_t ----
@@ -468,16 +507,19 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float cs = warp_colsum<W>(x, lane);
           if (lane < W) red2w[cbeg + lane] = cs;
         };
+        if (!DBG(p, 32)) {
         if constexpr (NH >= 32) pass_m(std::integral_constant<int, 32>{}, std::integral_constant<int, 0>{});
         if constexpr (NH == 64) pass_m(std::integral_constant<int, 32>{}, std::integral_constant<int, 32>{});
         if constexpr (NH == 40) pass_m(std::integral_constant<int, 8>{}, std::integral_constant<int, 32>{});
         if constexpr (NH == 16) pass_m(std::integral_constant<int, 16>{}, std::integral_constant<int, 0>{});
+        }
         tc_fence_before();
         mbar_arrive(m_free);
-        named_bar_sync(1, nsoft);
+        mbar_arrive(red_full);                                      // publishes this thread's red1/red2/Y entries
         // ---- serial tail, one warp, nobody waits for it (bookkeeping is double-buffered by pair parity):
         //      per-word cosine (losses.py:197-198), gamma2 log-sum-exp (:199-203), statistics for the backward ----
         if (warp == 0) {
+          mbar_wait(red_full, it & 1);
           const float *r1 = red1 + rb * 16 * NH, *r2 = red2 + rb * 16 * NH;
           const int64_t pair = (int64_t)i * p.bc + j;
           float *st = p.stats ? p.stats + pair * 3 * T : nullptr;
@@ -512,6 +554,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       } else {
         const float4 *vch = vcb + c0;
         const float *viyh = viyb + c0;
+        if (!DBG(p, 4)) {
         // ---- W = sum_t P dP with dP = gamma1 A (a S - b M)  (this row, all words: two halves via wbuf) ----
         float wp = 0.f;
 #pragma unroll
@@ -524,22 +567,23 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int k = 0; k < 8; k += 2) {
             const int tl = c * 8 + k;
             const float2 f = unpack_half2(e2p[tl >> 1]);
+            const float2 pp = unpack_half2(e1h[tl >> 1]);          // P
             const float4 ca = vch[tl], cb = vch[tl + 1];
-            wp = fmaf(e1[tl], f.x * (ca.x * xs[k] - ca.y * xm[k]), wp);
-            wp = fmaf(e1[tl + 1], f.y * (cb.x * xs[k + 1] - cb.y * xm[k + 1]), wp);
+            wp = fmaf(pp.x, f.x * (ca.x * xs[k] - ca.y * xm[k]), wp);
+            wp = fmaf(pp.y, f.y * (cb.x * xs[k + 1] - cb.y * xm[k + 1]), wp);
           }
         }
-        wbuf[half * 256 + widx] = wp * invZ;
-        named_bar_sync(1, nsoft);
-        const float Wr = wbuf[widx] + wbuf[256 + widx];
+        wb[half * 256 + widx] = wp;
+        named_bar_sync(2 + (warp & 7), 64);
+        const float Wr = wb[widx] + wb[256 + widx];
         // ---- dS = a A + P (dP - W); A; diag(b) A  -> scaled fp16 rows of the scratch matrices ----
-        {
+        if (!DBG(p, 2)) {
           const int64_t row = (int64_t)j * R + (valid ? rg : 0);
           const int64_t off = row * p.kc + (int64_t)blockIdx.x * p.tp + c0;
           uint4 *o_ds = reinterpret_cast<uint4 *>(p.x_ds + off);
           uint4 *o_a = reinterpret_cast<uint4 *>(p.x_a + off);
           uint4 *o_ba = reinterpret_cast<uint4 *>(p.x_ba + off);
-          const float sp = p.scale_ds * invZ;
+          const float sp = p.scale_ds;
 #pragma unroll
           for (int c = 0; c < NH / 8; ++c) {
             if (c0 + c * 8 < p.tp) {                                 // warp-uniform: tcgen05.ld is warp-collective
@@ -552,22 +596,25 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               for (int k = 0; k < 8; k += 2) {
                 const int tl = c * 8 + k;
                 const float2 f = unpack_half2(e2p[tl >> 1]);
+                const float2 pp = unpack_half2(e1h[tl >> 1]);
                 const float4 ca = vch[tl], cb = vch[tl + 1];
                 const float dp0 = f.x * (ca.x * xs[k] - ca.y * xm[k]);
                 const float dp1 = f.y * (cb.x * xs[k + 1] - cb.y * xm[k + 1]);
-                const float ds0 = fmaf(ca.z, f.x, sp * e1[tl] * (dp0 - Wr));
-                const float ds1 = fmaf(cb.z, f.y, sp * e1[tl + 1] * (dp1 - Wr));
+                const float ds0 = fmaf(ca.z, f.x, sp * pp.x * (dp0 - Wr));
+                const float ds1 = fmaf(cb.z, f.y, sp * pp.y * (dp1 - Wr));
                 pk_ds[k >> 1] = pack_half2_sat(ds0, ds1);
                 pk_a[k >> 1] = pack_half2(viyh[tl] * f.x, viyh[tl + 1] * f.y);
                 pk_ba[k >> 1] = pack_half2_sat(ca.w * f.x, cb.w * f.y);
               }
-              if (valid) {
-                o_ds[c] = make_uint4(pk_ds[0], pk_ds[1], pk_ds[2], pk_ds[3]);
-                o_a[c] = make_uint4(pk_a[0], pk_a[1], pk_a[2], pk_a[3]);
-                o_ba[c] = make_uint4(pk_ba[0], pk_ba[1], pk_ba[2], pk_ba[3]);
+              if (valid && !DBG(p, 1)) {
+                // streaming stores: the scratch is written once and read back by the GEMMs much later
+                __stcs(o_ds + c, make_uint4(pk_ds[0], pk_ds[1], pk_ds[2], pk_ds[3]));
+                __stcs(o_a + c, make_uint4(pk_a[0], pk_a[1], pk_a[2], pk_a[3]));
+                __stcs(o_ba + c, make_uint4(pk_ba[0], pk_ba[1], pk_ba[2], pk_ba[3]));
               }
             }
           }
+        }
         }
         tc_fence_before();
         mbar_arrive(&s_free[b]);
@@ -742,6 +789,7 @@ extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void
   TcParams p{};
   p.br = (int)br; p.bc = (int)bc; p.T = (int)t; p.R = (int)r; p.D = (int)d;
   p.g1 = gamma1; p.g2 = gamma2; p.g3 = gamma3; p.mask = mask; p.unorm = unorm; p.sim = sim; p.stats = stats;
+  p.dbg = getenv("DAMSM_DBG") ? atoi(getenv("DAMSM_DBG")) : 0;
   return tc_launch<false>(tl, p, br, (cudaStream_t)stream);
 }
 
@@ -797,6 +845,7 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
     p.i0 = (int)i0; p.tp = (int)tp; p.kc = kc; p.row_lse = row_lse; p.col_lse = col_lse; p.gscale = gscale;
     p.labels = labels; p.row_offset = row_offset; p.b_total = b_total; p.kq = kq;
     p.x_ds = x_ds; p.x_a = x_a; p.x_ba = x_ba; p.scale_ds = scale_ds; p.scale_ba = scale_ba;
+    p.dbg = getenv("DAMSM_DBG") ? atoi(getenv("DAMSM_DBG")) : 0;
     if ((rc = tc_launch<true>(tl, p, bi, st))) return rc;
     if (getenv("DAMSM_DEBUG_SYNC")) {
       cudaError_t e = cudaStreamSynchronize(st);
