@@ -5,7 +5,7 @@ SRC := $(wildcard $(PKG)/csrc/*.cu)
 HDR := $(wildcard $(PKG)/csrc/*.cuh) include/damsm_b200.h
 OUT := $(PKG)/libdamsm_b200.so
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC \
-           -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr
+           -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr $(EXTRA)
 
 all: $(OUT)
 

@@ -27,12 +27,40 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+#ifdef DAMSM_SPIN_WAIT
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+#else
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+#endif
       "selp.b32 %0, 1, 0, P1;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware, do not spin
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
+}
+// Non-suspending probe, for the single-thread roles (TMA producer, MMA issuer): a suspended try_wait wakes up with
+// a coarse granularity, which puts microseconds on every hop of the operand ring.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity) {
+  if (mbar_test_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_test_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("damsm: mbarrier spin timed out (block %d thread %d bar %p parity %u)\n", blockIdx.x, threadIdx.x,
+             (void *)bar, parity);
+      __trap();
+    }
+  }
 }
 // Bounded wait: a protocol bug must surface as a trapped launch (error code), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
@@ -130,6 +158,19 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       :
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// same, with the descriptors passed as (low word, shared high word): the low word carries the start address
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                              bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed

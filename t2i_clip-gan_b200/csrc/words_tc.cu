@@ -57,9 +57,9 @@ __host__ __device__ inline TcLayout tc_layout(int NT, int R, int D) {
   // the overrun of the last stage may reach into the e2 buffer but not into the fp32 bookkeeping behind it.
   if ((uint32_t)l.tiles * 16384 > l.stage_bytes + l.e2_bytes) l.stage_bytes = (uint32_t)l.tiles * 16384;
   l.misc_off = l.q_bytes + TC_STAGES * l.stage_bytes + l.e2_bytes;
-  // misc: 256 B of barriers / scalars, then floats: u,tb,tb2 [NT] + iy,Y [2][NT] + vc float4 [2][NT] +
-  // red1/red2 [2][16][NT/2] + zbuf/wbuf [2][256]   ([2] = double-buffered by pair parity)
-  l.total = l.misc_off + 256 + 4 * (7 * NT + 8 * NT + 32 * NT + 2048) + 1024 /*alignment slack*/;
+  // misc: 256 B of barriers / scalars, then floats: u,tb,tb2 [NT] + iy [2][NT] + Y [3][NT] + vc float4 [2][NT] +
+  // red1/red2 [3][NT][8] + zbuf/wbuf [2][2][256]   ([2]/[3] = multi-buffered by pair index, see fwd_tail)
+  l.total = l.misc_off + 256 + 4 * (8 * NT + 8 * NT + 48 * NT + 2048) + 1024 /*alignment slack*/;
   return l;
 }
 
@@ -67,8 +67,10 @@ __host__ __device__ inline TcLayout tc_layout(int NT, int R, int D) {
 // 1 no scratch stores, 2 no sweep 2, 4 no sweeps, 8/16 skip Gx / vhat TMA loads, 32 no softmax math, 64 no MMAs.
 #ifdef DAMSM_TC_DEBUG
 #define DBG(p, bit) ((p).dbg & (bit))
+#define TRACE(p, slot, it, k) do { if ((p).trace && blockIdx.x == 0 && blockIdx.y == 0 && (it) < 16) (p).trace[((slot) * 16 + (it)) * 8 + (k)] = clock64(); } while (0)
 #else
 #define DBG(p, bit) (0)
+#define TRACE(p, slot, it, k) do {} while (0)
 #endif
 
 struct TcParams {
@@ -89,6 +91,7 @@ struct TcParams {
   float *kq;
   __half *x_ds, *x_a, *x_ba;          // scratch matrices [(j, r)][(i_local, t)], fp16
   float scale_ds, scale_ba;           // power-of-two scales that keep dS and diag(b)A in fp16's normal range
+  long long *trace;                   // development: clock64 trace buffer (debug builds only)
   int dbg;                            // development switches (env DAMSM_DBG): 1 no stores, 2 no sweep 2, 4 no sweeps
 };
 
@@ -202,10 +205,10 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float *vu = reinterpret_cast<float *>(misc + 256);          // [NT] ||qhat_t||
   float *tb = vu + NT;                                        // 0 for real words, -inf for padding and t >= T
   float *tb2 = tb + NT;                                       // 0 for t < T, -inf for t >= T
-  float *viy = tb2 + NT, *vY = viy + 2 * NT;                  // [2][NT] each: 1/Y (backward), Y (forward)
-  float4 *vc = reinterpret_cast<float4 *>(vY + 2 * NT);       // [2][NT] backward coefficients
-  float *red1 = reinterpret_cast<float *>(vc + 2 * NT), *red2 = red1 + 32 * NH;   // [2][16][NH] each
-  float *zbuf = red2 + 32 * NH, *wbuf = zbuf + 1024;          // [2 parities][2 halves][256] each
+  float *viy = tb2 + NT, *vY = viy + 2 * NT;                  // 1/Y [2][NT] (backward), Y [3][NT] (forward)
+  float4 *vc = reinterpret_cast<float4 *>(vY + 3 * NT);       // [2][NT] backward coefficients
+  float *red1 = reinterpret_cast<float *>(vc + 2 * NT), *red2 = red1 + 24 * NT;   // [3][NT][8] each
+  float *zbuf = red2 + 24 * NT, *wbuf = zbuf + 1024;          // [2 parities][2 halves][256] each
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = (BWD ? p.i0 : 0) + blockIdx.x;
@@ -221,8 +224,11 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(q_full, 1); mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(m_full, 1);
-    mbar_init(&s_free[0], nsoft); mbar_init(&s_free[1], nsoft);
-    mbar_init(e2_ready, nsoft); mbar_init(m_free, nsoft); mbar_init(red_full, nsoft); mbar_init(coef_full, 1);
+    // the softmax warps arrive once per warp (lane 0 after __syncwarp): 448 per-thread arrivals on one shared-memory
+    // word serialise and were the longest item of the per-pair critical path
+    mbar_init(&s_free[0], L.act_warps); mbar_init(&s_free[1], L.act_warps);
+    mbar_init(e2_ready, L.act_warps); mbar_init(m_free, L.act_warps); mbar_init(red_full, L.act_warps);
+    mbar_init(coef_full, 1);
     fence_barrier_init();
   }
   for (int t = threadIdx.x; t < NT; t += TC_THREADS) {
@@ -232,6 +238,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tb2[t] = in ? 0.f : -INFINITY;
     vc[t] = vc[NT + t] = make_float4(0.f, 0.f, 0.f, 0.f);
     viy[t] = viy[NT + t] = 0.f;
+    for (int k = 0; k < 24; ++k) red1[t * 24 + k] = red2[t * 24 + k] = 0.f;   // [3][NT][8]: unused warp slots stay 0
   }
   if (warp == MMA_WARP) tmem_alloc<512>(tmem_ptr);
   if (warp == TMA_WARP && lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmV); prefetch_tmap(&tmG); }
@@ -277,46 +284,67 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (elect_one()) {
       mbar_wait(q_full, 0);
       int stage = 0, phase = 0;
+      // The issuing thread is a single lane: its instruction latency, not the tensor pipe, bounded the per-pair time
+      // when every MMA rebuilt two 64-bit descriptors.  Keep the constant high words and base low words in registers.
+      const uint64_t dproto = umma_desc_k_sw128(0);
+      const uint32_t desc_hi = (uint32_t)(dproto >> 32);
+      const uint32_t dlo = (uint32_t)dproto;
+      const uint32_t a_lo0 = dlo + (smem_u32(stages) >> 4), q_lo0 = dlo + (smem_u32(Qs) >> 4), e_lo0 = dlo + (smem_u32(E2) >> 4);
+      const uint32_t stage_units = L.stage_bytes >> 4, kb_units = (uint32_t)(NT * 128) >> 4;
+      const bool two_tiles = L.tiles == 2;
       auto gemm1 = [&](int it) {                       // S^T[buf] = vhat_j qhat_i^T
         const int b = it % nbuf, use = it / nbuf;
         if (use > 0) mbar_wait(&s_free[b], (use - 1) & 1);
         tc_fence_after();
+        TRACE(p, 0, it, 0);
         const uint32_t d0 = tmem_base + (uint32_t)(b * L.tiles * NT);
         for (int kb = 0; kb < L.nkb_d; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a0 = smem_u32(stages + stage * L.stage_bytes), b0 = smem_u32(Qs + kb * NT * 128);
+          // descriptors differ only in the 14-bit start-address field (16-byte units): one add per operand
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_units, b_lo = q_lo0 + (uint32_t)kb * kb_units;
+          if (!DBG(p, 64)) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            for (int tl = 0; tl < L.tiles; ++tl)
-              if (!DBG(p, 64))
-              umma_f16(d0 + tl * NT, umma_desc_k_sw128(a0 + tl * 16384 + k * 32), umma_desc_k_sw128(b0 + k * 32),
-                       idesc, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k) {
+              umma_f16_lohi(d0, a_lo + k * 2, b_lo + k * 2, desc_hi, idesc, (kb | k) != 0);
+              if (two_tiles) umma_f16_lohi(d0 + NT, a_lo + 1024 + k * 2, b_lo + k * 2, desc_hi, idesc, (kb | k) != 0);
+            }
+          }
+          if (DBG(p, 128)) mbar_arrive(&empty[stage]); else
           umma_commit(&empty[stage]);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&s_full[b]);
+        TRACE(p, 0, it, 1);
       };
       auto gemm2 = [&](int it) {                       // M'^T = Gx_j e2
         mbar_wait(e2_ready, it & 1);
         if (it > 0) mbar_wait(m_free, (it - 1) & 1);
         tc_fence_after();
+        TRACE(p, 0, it, 2);
         int left = L.k2_steps;
+        const uint32_t dm = tmem_base + col_m;
         for (int kb = 0; kb < L.nkb_r; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a0 = smem_u32(stages + stage * L.stage_bytes), b0 = smem_u32(E2 + kb * NT * 128);
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_units, b_lo = e_lo0 + (uint32_t)kb * kb_units;
           const int nk = min(4, left);
-          for (int k = 0; k < nk; ++k)
-            for (int tl = 0; tl < L.tiles; ++tl)
-              if (!DBG(p, 64))
-              umma_f16(tmem_base + col_m + tl * NT, umma_desc_k_sw128(a0 + tl * 16384 + k * 32),
-                       umma_desc_k_sw128(b0 + k * 32), idesc, (kb | k) != 0);
+          if (!DBG(p, 64)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < nk) {
+                umma_f16_lohi(dm, a_lo + k * 2, b_lo + k * 2, desc_hi, idesc, (kb | k) != 0);
+                if (two_tiles) umma_f16_lohi(dm + NT, a_lo + 1024 + k * 2, b_lo + k * 2, desc_hi, idesc, (kb | k) != 0);
+              }
+            }
+          }
           left -= nk;
+          if (DBG(p, 128)) mbar_arrive(&empty[stage]); else
           umma_commit(&empty[stage]);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(m_full);
+        TRACE(p, 0, it, 3);
       };
       const int n = j1 - j0;
       if (nbuf == 2) {
@@ -349,7 +377,8 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     const float4 *tb4 = reinterpret_cast<const float4 *>(tb + c0);
     const float2 *tb22 = reinterpret_cast<const float2 *>(tb2 + c0);
-    float *red1w0 = red1 + warp * NH, *red2w0 = red2 + warp * NH;
+    // cross-warp partial sums, laid out [parity][word t][8 warps of that word's half] so the tail reads float4s
+    float *red1w0 = red1 + (half * NH) * 8 + (warp & 7), *red2w0 = red2 + (half * NH) * 8 + (warp & 7);
     const int widx = (warp & 7) * 32 + lane;                        // row slot in zbuf / wbuf
     constexpr int CPL = (NT + 31) / 32;                             // words per lane in the one-warp sections
     // backward, warp 0: per-row constants of dL/dsim (both cross-entropies, losses.py:265-269)
@@ -362,30 +391,61 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       bw_g0 = p.gscale[0]; bw_g1 = p.gscale[1];
       bw_ib = 1.f / (float)p.b_total;
     }
-    for (int j = j0, it = 0; j < j1; ++j, ++it) {
-      const int b = it % nbuf;
-      const uint32_t t_s = t_lane + (uint32_t)(b * L.tiles * NT);
-      float e1[NH];
-      uint32_t e2p[NH / 2];
-      const int rb = it & 1;                                        // parity of the double-buffered bookkeeping
-      float *red1w = red1w0 + rb * 16 * NH, *red2w = red2w0 + rb * 16 * NH;
-      float *vYb = vY + rb * NT;
-      float4 *vcb = vc + rb * NT;
-      float *viyb = viy + rb * NT;
-      mbar_wait(&s_full[b], (it / nbuf) & 1);
+    // ---- serial tail of the forward, one warp: per-word cosine (losses.py:197-198), gamma2 log-sum-exp (:199-203),
+    //      statistics for the backward.  It runs one pair late, while GEMM2 of the next pair is in flight (every warp
+    //      idles there), so it is off the critical path; the bookkeeping it reads is double-buffered by pair parity.
+    auto fwd_tail = [&](int it_, int j_) {
+      const int rb_ = it_ % 3;
+      mbar_wait(red_full, it_ & 1);
+      const float4 *r1 = reinterpret_cast<const float4 *>(red1 + rb_ * NT * 8);
+      const float4 *r2 = reinterpret_cast<const float4 *>(red2 + rb_ * NT * 8);
+      const float *vYb_ = vY + rb_ * NT;
+      const int64_t pair = (int64_t)i * p.bc + j_;
+      float *st = p.stats ? p.stats + pair * 3 * T : nullptr;
+      float xv[CPL];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) {
+        const int t = q * 32 + lane;
+        xv[q] = -INFINITY;
+        if (t < T) {
+          const float4 a0 = r1[2 * t], a1 = r1[2 * t + 1], b0 = r2[2 * t], b1 = r2[2 * t + 1];
+          const float np = ((a0.x + a0.y) + (a0.z + a0.w)) + ((a1.x + a1.y) + (a1.z + a1.w));
+          const float nn = ((b0.x + b0.y) + (b0.z + b0.w)) + ((b1.x + b1.y) + (b1.z + b1.w));
+          const float iy = 1.f / vYb_[t];
+          const float n = sqrtf(fmaxf(nn, 0.f)) * iy;
+          const float rho = (np * iy) / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
+          if (st) { st[t] = rho; st[T + t] = n; st[2 * T + t] = iy; }
+          xv[q] = p.g2 * rho;
+          mx = fmaxf(mx, xv[q]);
+        }
+      }
+      mx = warp_max(mx);
+      float se = 0.f;
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) se += __expf(xv[q] - mx);       // exp(-inf) = 0 for the unused slots
+      se = warp_sum(se);
+      if (lane == 0) p.sim[pair] = p.g3 * ((__logf(se) + mx) / p.g2);
+    };
+    // ---- pass A of pair `it_`: e1 = exp(S + mask bias), Z = sum_t e1 (softmax over words, losses.py:127,143-144).
+    //      Forward runs it for the NEXT pair while GEMM2 of the current one is in flight (e1 of the current pair is
+    //      dead after pass B), backward right after the sweeps.
+    float e1[NH];
+    float invZ = 0.f, k2 = 0.f;
+    auto pass_a = [&](int it_) {
+      const int b_ = it_ % nbuf;
+      const uint32_t ts_ = t_lane + (uint32_t)(b_ * L.tiles * NT);
+      mbar_wait(&s_full[b_], (it_ / nbuf) & 1);
       tc_fence_after();
-      // ---- pass A: e1 = exp(S + mask bias), Z = sum_t e1 (softmax over words, losses.py:127,143-144) ----
       float zp = 0.f;
       if (DBG(p, 32)) {
 #pragma unroll
         for (int c = 0; c < NH; ++c) e1[c] = 1.f;
-#pragma unroll
-        for (int c = 0; c < NH / 2; ++c) e2p[c] = 0;
       } else
 #pragma unroll
       for (int c = 0; c < NH / 8; ++c) {
         float x[8];
-        tmem_ld<8>(t_s + c * 8, x);
+        tmem_ld<8>(ts_ + c * 8, x);
         const float4 ba = tb4[2 * c], bb = tb4[2 * c + 1];
         const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
@@ -395,13 +455,30 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           zp += e;
         }
       }
-      float *zb = zbuf + rb * 512, *wb = wbuf + rb * 512;
+      float *zb = zbuf + (it_ & 1) * 512;
       zb[half * 256 + widx] = zp;
       // only the two warps that share these rows (word halves) exchange Z: a 64-thread named barrier per pair
       named_bar_sync(2 + (warp & 7), 64);
-      const float Z = zb[widx] + zb[256 + widx];
-      const float invZ = 1.f / Z;
-      const float k2 = p.g1 * kLog2e * invZ;
+      invZ = 1.f / (zb[widx] + zb[256 + widx]);
+      k2 = p.g1 * kLog2e * invZ;
+    };
+    if (j0 < j1) pass_a(0);
+    for (int j = j0, it = 0; j < j1; ++j, ++it) {
+      const int b = it % nbuf;
+      const uint32_t t_s = t_lane + (uint32_t)(b * L.tiles * NT);
+      uint32_t e2p[NH / 2];
+      const int rb = it & 1;                                        // parity of the double-buffered bookkeeping
+      const int rb3 = it % 3;                                       // the forward tail runs one pair late: 3 buffers
+      float *red1w = red1w0 + rb3 * NT * 8, *red2w = red2w0 + rb3 * NT * 8;
+      float *vYb = vY + rb3 * NT;
+      float4 *vcb = vc + rb * NT;
+      float *viyb = viy + rb * NT;
+      float *wb = wbuf + rb * 512;
+      if (DBG(p, 32)) {
+#pragma unroll
+        for (int c = 0; c < NH / 2; ++c) e2p[c] = 0;
+      }
+      if (warp == 1 && lane == 0) TRACE(p, 1, it, 1);
       // ---- pass B: e2 = exp(gamma1 P) (softmax over regions, un-normalised) -> fp16 B operand of GEMM2;
       //      forward also forms the N' = sum_r e2 S partial sums ----
       auto pass_b = [&](auto width, auto cb) {
@@ -429,7 +506,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         if constexpr (!BWD) {
           const float cs = warp_colsum<W>(x, lane);
-          if (lane < W) red1w[cbeg + lane] = cs;
+          if (lane < W) red1w[(cbeg + lane) * 8] = cs;
         }
       };
       if (!DBG(p, 32)) {
@@ -447,8 +524,11 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(e2_ready);
-      if (!BWD) mbar_arrive(&s_free[b]);                            // forward: S is dead from here on
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(e2_ready);
+        if (!BWD) mbar_arrive(&s_free[b]);                          // forward: S is dead from here on
+      }
       if constexpr (BWD) {
         // ---- warp 0: per-word coefficients from the statistics the forward saved (rho, ||c||, 1/Y):
         //      beta = dL/drho, a = beta/(n u), b = beta rho / n^2.  Runs while GEMM2 is in flight; the sweeps of every
@@ -484,8 +564,14 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if constexpr (BWD) {
         if (warp == 0) { __syncwarp(); if (lane == 0) mbar_arrive(coef_full); }
       }
+      if (warp == 1 && lane == 0) TRACE(p, 1, it, 2);
+      if constexpr (!BWD) {
+        if (j + 1 < j1) pass_a(it + 1);                             // fills the GEMM2 bubble
+        if (warp == 0 && it > 0) fwd_tail(it - 1, j - 1);
+      }
       mbar_wait(m_full, it & 1);
       if constexpr (BWD) mbar_wait(coef_full, it & 1);
+      if (warp == 1 && lane == 0) TRACE(p, 1, it, 3);
       tc_fence_after();
       if constexpr (!BWD) {
         // ---- NN = sum_r e2 M' partial sums; the appended ones-row delivers Y_t ----
@@ -505,7 +591,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             x[k + 1] *= f.y;
           }
           const float cs = warp_colsum<W>(x, lane);
-          if (lane < W) red2w[cbeg + lane] = cs;
+          if (lane < W) red2w[(cbeg + lane) * 8] = cs;
         };
         if (!DBG(p, 32)) {
         if constexpr (NH >= 32) pass_m(std::integral_constant<int, 32>{}, std::integral_constant<int, 0>{});
@@ -514,43 +600,12 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if constexpr (NH == 16) pass_m(std::integral_constant<int, 16>{}, std::integral_constant<int, 0>{});
         }
         tc_fence_before();
-        mbar_arrive(m_free);
-        mbar_arrive(red_full);                                      // publishes this thread's red1/red2/Y entries
-        // ---- serial tail, one warp, nobody waits for it (bookkeeping is double-buffered by pair parity):
-        //      per-word cosine (losses.py:197-198), gamma2 log-sum-exp (:199-203), statistics for the backward ----
-        if (warp == 0) {
-          mbar_wait(red_full, it & 1);
-          const float *r1 = red1 + rb * 16 * NH, *r2 = red2 + rb * 16 * NH;
-          const int64_t pair = (int64_t)i * p.bc + j;
-          float *st = p.stats ? p.stats + pair * 3 * T : nullptr;
-          float xv[CPL];
-          float mx = -INFINITY;
-#pragma unroll
-          for (int q = 0; q < CPL; ++q) {
-            const int t = q * 32 + lane;
-            xv[q] = -INFINITY;
-            if (t < T) {
-              const int h = t / NH, tl = t - h * NH;
-              float np = 0.f, nn = 0.f;
-              for (int w = 0; w < L.act_warps / 2; ++w) {
-                np += r1[(h * 8 + w) * NH + tl];
-                nn += r2[(h * 8 + w) * NH + tl];
-              }
-              const float iy = 1.f / vYb[t];
-              const float n = sqrtf(fmaxf(nn, 0.f)) * iy;
-              const float rho = (np * iy) / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
-              if (st) { st[t] = rho; st[T + t] = n; st[2 * T + t] = iy; }
-              xv[q] = p.g2 * rho;
-              mx = fmaxf(mx, xv[q]);
-            }
-          }
-          mx = warp_max(mx);
-          float se = 0.f;
-#pragma unroll
-          for (int q = 0; q < CPL; ++q) se += __expf(xv[q] - mx);   // exp(-inf) = 0 for the unused slots
-          se = warp_sum(se);
-          if (lane == 0) p.sim[pair] = p.g3 * ((__logf(se) + mx) / p.g2);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(m_free);
+          mbar_arrive(red_full);                                    // publishes this warp's red1/red2/Y entries
         }
+        if (warp == 1 && lane == 0) TRACE(p, 1, it, 4);
       } else {
         const float4 *vch = vcb + c0;
         const float *viyh = viyb + c0;
@@ -617,9 +672,16 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         }
         tc_fence_before();
-        mbar_arrive(&s_free[b]);
-        mbar_arrive(m_free);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&s_free[b]);
+          mbar_arrive(m_free);
+        }
+        if (j + 1 < j1) pass_a(it + 1);
       }
+    }
+    if constexpr (!BWD) {
+      if (warp == 0 && j1 > j0) fwd_tail(j1 - j0 - 1, j1 - 1);
     }
   }
   tc_fence_before();
@@ -790,6 +852,25 @@ extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void
   p.br = (int)br; p.bc = (int)bc; p.T = (int)t; p.R = (int)r; p.D = (int)d;
   p.g1 = gamma1; p.g2 = gamma2; p.g3 = gamma3; p.mask = mask; p.unorm = unorm; p.sim = sim; p.stats = stats;
   p.dbg = getenv("DAMSM_DBG") ? atoi(getenv("DAMSM_DBG")) : 0;
+#ifdef DAMSM_TC_DEBUG
+  if (getenv("DAMSM_TRACE")) {
+    static long long *tr = nullptr;
+    if (!tr) cudaMalloc(&tr, 3 * 16 * 8 * sizeof(long long));
+    cudaMemsetAsync(tr, 0, 3 * 16 * 8 * sizeof(long long), (cudaStream_t)stream);
+    p.trace = tr;
+    int rc2 = tc_launch<false>(tl, p, br, (cudaStream_t)stream);
+    long long h[3 * 16 * 8];
+    cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost);
+    long long t0 = h[0];
+    for (int it = 0; it < 12; ++it) {
+      fprintf(stderr, "it %2d MMA: g1start %7lld g1issued %7lld g2start %7lld g2issued %7lld | SM: s_full %7lld passA %7lld arrive %7lld m_full %7lld passM %7lld | tail %7lld\n", it,
+              h[(0 * 16 + it) * 8 + 0] - t0, h[(0 * 16 + it) * 8 + 1] - t0, h[(0 * 16 + it) * 8 + 2] - t0, h[(0 * 16 + it) * 8 + 3] - t0,
+              h[(1 * 16 + it) * 8 + 0] - t0, h[(1 * 16 + it) * 8 + 1] - t0, h[(1 * 16 + it) * 8 + 2] - t0, h[(1 * 16 + it) * 8 + 3] - t0, h[(1 * 16 + it) * 8 + 4] - t0,
+              h[(2 * 16 + it) * 8 + 0] - t0);
+    }
+    return rc2;
+  }
+#endif
   return tc_launch<false>(tl, p, br, (cudaStream_t)stream);
 }
 
