@@ -131,8 +131,9 @@ class CudaEngine:
         _lib.call("damsm_gram_bwd_f32", hmat.data_ptr(), vhat.data_ptr(), bc, r, d, dvhat.data_ptr(), _stream())
         return dqhat, dvhat, kq
 
-    # scratch for the tensor-core backward (bytes); the fused kernel + GEMMs run chunk by chunk inside it
-    tc_workspace_bytes = 6 << 30
+    # scratch for the tensor-core backward: the fused kernel + GEMMs run chunk by chunk inside it.  Larger chunks
+    # mean fewer launches and a longer K for the gradient GEMMs; default = a third of the free HBM, at least 6 GiB.
+    tc_workspace_bytes = None
 
     def _words_bwd_tc(self, qhat16, vhat, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
                       row_offset, b_total, gammas, br, bc, t, r, d):
@@ -140,7 +141,10 @@ class CudaEngine:
         tp = qhat16.shape[1]
         lib = _lib.load()
         row_bytes = lib.damsm_words_bwd_tc_row_bytes(bc, t, r)
-        ws_bytes = min(max(row_bytes, self.tc_workspace_bytes // row_bytes * row_bytes), row_bytes * br)
+        budget = self.tc_workspace_bytes
+        if budget is None:
+            budget = max(6 << 30, torch.cuda.mem_get_info(dev)[0] // 3)
+        ws_bytes = min(max(row_bytes, budget // row_bytes * row_bytes), row_bytes * br)
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         dqhat = torch.empty((br, tp, d), device=dev, dtype=torch.float32)
         dvhat = torch.zeros((bc, r, d), device=dev, dtype=torch.float32)

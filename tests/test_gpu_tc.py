@@ -60,3 +60,29 @@ def test_tc_words_loss_and_grads(B, T, R, cls, seed):
     assert abs(l1.item() - o["loss1"]) <= TOL * max(1, abs(o["loss1"]))
     assert rel(w.grad.cpu().numpy(), o["dwords"]) <= TOL
     assert rel(r.grad.cpu().numpy(), o["dregions"]) <= TOL
+
+
+def test_tc_multi_chunk_backward_matches_exact_path():
+    """Larger batch, backward forced through several workspace chunks and several image splits per caption:
+    tensor-core gradients against the exact fp32 CUDA path (itself pinned to the oracle) on the same inputs."""
+    B, T, R = 96, 77, 196
+    x = rounded(O.make_inputs(B, T, R, seed=21, class_ids=True, n_classes=7))
+    eng = pkg.get_engine("bf16")
+    lib = pkg._lib.load()
+    old = eng.tc_workspace_bytes
+    eng.tc_workspace_bytes = 20 * lib.damsm_words_bwd_tc_row_bytes(B, T, R)      # 96 rows -> 5 chunks (20,20,20,20,16)
+    try:
+        res = {}
+        for prec in ("fp32", "bf16"):
+            w = torch.tensor(x["words"], device="cuda").requires_grad_(True)
+            r = torch.tensor(x["regions"], device="cuda").requires_grad_(True)
+            l0, l1, _ = pkg.words_loss(r.permute(0, 2, 1), w.permute(0, 2, 1), torch.arange(B, device="cuda"), None,
+                                       x["class_ids"], B, torch.tensor(x["mask"]), 4.0, 5.0, 10.0, precision=prec)
+            (l0 + 0.5 * l1).backward()
+            res[prec] = (l0.item(), l1.item(), w.grad.cpu().numpy(), r.grad.cpu().numpy())
+    finally:
+        eng.tc_workspace_bytes = old
+    a, b = res["bf16"], res["fp32"]
+    assert abs(a[0] - b[0]) <= TOL * max(1, abs(b[0])) and abs(a[1] - b[1]) <= TOL * max(1, abs(b[1]))
+    assert rel(a[2], b[2]) <= TOL
+    assert rel(a[3], b[3]) <= TOL
