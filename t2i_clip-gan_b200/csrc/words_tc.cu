@@ -89,7 +89,8 @@ struct TcParams {
   const int64_t *labels;
   int64_t row_offset, b_total;
   float *kq;
-  __half *x_ds, *x_a, *x_ba;          // scratch matrices [(j, r)][(i_local, t)], fp16
+  __half *x_ds, *x_a;                 // scratch matrices [(j, r)][(i_local, t)], fp16: scaled dS, and A
+  float *svec;                        // (bc, kc): scale_ba * b_t per (image, caption, word), for the H kernel
   float scale_ds, scale_ba;           // power-of-two scales that keep dS and diag(b)A in fp16's normal range
   long long *trace;                   // development: clock64 trace buffer (debug builds only)
   int dbg;                            // development switches (env DAMSM_DBG): 1 no stores, 2 no sweep 2, 4 no sweeps
@@ -554,9 +555,12 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               const float beta = g * p.g3 * omega;                  // dL/drho_t
               const float a = beta / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
               const float bq = (n > kCosEps) ? beta * rho / (n * n) : 0.f;
-              vcb[t] = make_float4(p.g1 * a * iy, p.g1 * bq * iy * iy, a * iy * p.scale_ds, bq * iy * p.scale_ba);
+              vcb[t] = make_float4(p.g1 * a * iy, p.g1 * bq * iy * iy, a * iy * p.scale_ds, 0.f);
+              p.svec[(int64_t)j * p.kc + (int64_t)blockIdx.x * p.tp + t] = bq * p.scale_ba;
               viyb[t] = iy;
               atomicAdd(p.kq + (int64_t)i * T + t, beta * rho);
+            } else if (t < p.tp) {
+              p.svec[(int64_t)j * p.kc + (int64_t)blockIdx.x * p.tp + t] = 0.f;
             }
           }
         }
@@ -637,7 +641,6 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const int64_t off = row * p.kc + (int64_t)blockIdx.x * p.tp + c0;
           uint4 *o_ds = reinterpret_cast<uint4 *>(p.x_ds + off);
           uint4 *o_a = reinterpret_cast<uint4 *>(p.x_a + off);
-          uint4 *o_ba = reinterpret_cast<uint4 *>(p.x_ba + off);
           const float sp = p.scale_ds;
 #pragma unroll
           for (int c = 0; c < NH / 8; ++c) {
@@ -646,7 +649,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               tmem_ld8_issue(t_s + c * 8, xs);
               tmem_ld8_issue(t_m + c * 8, xm);
               tmem_wait16(xs, xm);
-              uint32_t pk_ds[4], pk_a[4], pk_ba[4];
+              uint32_t pk_ds[4], pk_a[4];
 #pragma unroll
               for (int k = 0; k < 8; k += 2) {
                 const int tl = c * 8 + k;
@@ -659,13 +662,11 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const float ds1 = fmaf(cb.z, f.y, sp * pp.y * (dp1 - Wr));
                 pk_ds[k >> 1] = pack_half2_sat(ds0, ds1);
                 pk_a[k >> 1] = pack_half2(viyh[tl] * f.x, viyh[tl + 1] * f.y);
-                pk_ba[k >> 1] = pack_half2_sat(ca.w * f.x, cb.w * f.y);
               }
               if (valid && !DBG(p, 1)) {
                 // streaming stores: the scratch is written once and read back by the GEMMs much later
                 __stcs(o_ds + c, make_uint4(pk_ds[0], pk_ds[1], pk_ds[2], pk_ds[3]));
                 __stcs(o_a + c, make_uint4(pk_a[0], pk_a[1], pk_a[2], pk_a[3]));
-                __stcs(o_ba + c, make_uint4(pk_ba[0], pk_ba[1], pk_ba[2], pk_ba[3]));
               }
             }
           }
@@ -707,7 +708,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 // fp16 tensor (n2, n1, n0), rows `pitch1` and slabs `pitch2` elements apart; box (1, box1, 64), 128-byte swizzle
-static int make_map_f16(CUtensorMap *m, const void *base, uint64_t n0, uint64_t n1, uint64_t n2, uint64_t pitch1_elems,
+int make_map_f16(CUtensorMap *m, const void *base, uint64_t n0, uint64_t n1, uint64_t n2, uint64_t pitch1_elems,
                         uint64_t pitch2_elems, uint32_t box1) {
   PFN_encodeTiled enc = get_encode();
   DAMSM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
@@ -805,6 +806,9 @@ static int tc_launch(const TcLaunch &tl, TcParams &p, int64_t rows, cudaStream_t
   return check_launch(BWD ? "words_bwd_tc (fused recompute)" : "words_fwd_tc");
 }
 
+int launch_hmat_tc(const void *x_a, const float *svec, int64_t bc, int64_t r, int64_t kc, float alpha, float *hmat,
+                   cudaStream_t st);   // hmat_tc.cu
+
 static cublasHandle_t get_cublas() {
   static thread_local cublasHandle_t h = nullptr;
   if (!h && cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) h = nullptr;
@@ -874,10 +878,10 @@ extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void
   return tc_launch<false>(tl, p, br, (cudaStream_t)stream);
 }
 
-// bytes of scratch per caption row of a chunk: three fp16 matrices [(j,r)][t_pad]
+// bytes of scratch per caption row of a chunk: two fp16 matrices [(j,r)][t_pad] + the per-word scales (bc, t_pad) fp32
 extern "C" int64_t damsm_words_bwd_tc_row_bytes(int64_t bc, int64_t t, int64_t r) {
   const int64_t tp = (t + 7) / 8 * 8;
-  return 3 * tp * bc * r * 2;
+  return 2 * tp * bc * r * 2 + tp * bc * 4;
 }
 
 extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
@@ -918,14 +922,14 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
     const int64_t kc = bi * tp;
     __half *x_ds = (__half *)workspace;
     __half *x_a = x_ds + n_rows * kc;
-    __half *x_ba = x_a + n_rows * kc;
+    float *svec = reinterpret_cast<float *>(x_a + n_rows * kc);
     TcParams p{};
     p.br = (int)br; p.bc = (int)bc; p.T = (int)t; p.R = (int)r; p.D = (int)d;
     p.g1 = gamma1; p.g2 = gamma2; p.g3 = gamma3; p.mask = mask; p.unorm = unorm; p.sim = const_cast<float *>(sim);
     p.stats = const_cast<float *>(stats);
     p.i0 = (int)i0; p.tp = (int)tp; p.kc = kc; p.row_lse = row_lse; p.col_lse = col_lse; p.gscale = gscale;
     p.labels = labels; p.row_offset = row_offset; p.b_total = b_total; p.kq = kq;
-    p.x_ds = x_ds; p.x_a = x_a; p.x_ba = x_ba; p.scale_ds = scale_ds; p.scale_ba = scale_ba;
+    p.x_ds = x_ds; p.x_a = x_a; p.svec = svec; p.scale_ds = scale_ds; p.scale_ba = scale_ba;
     p.dbg = getenv("DAMSM_DBG") ? atoi(getenv("DAMSM_DBG")) : 0;
     if ((rc = tc_launch<true>(tl, p, bi, st))) return rc;
     if (getenv("DAMSM_DEBUG_SYNC")) {
@@ -942,10 +946,8 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
     DAMSM_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, (int)d, (int)kc, (int)n_rows, &inv_ds, vhat16, CUDA_R_16F,
                               (int)d, x_ds, CUDA_R_16F, (int)kc, &zero, dqhat + i0 * tp * d, CUDA_R_32F, (int)d,
                               CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT_TENSOR_OP));
-    // H_j (R x R) += A_j (R x kc) . (bA)_j^T (kc x R), batched over images
-    DAMSM_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_T, CUBLAS_OP_N, (int)r, (int)r, (int)kc, &inv_ba, x_a, CUDA_R_16F,
-                                            (int)kc, r * kc, x_ba, CUDA_R_16F, (int)kc, r * kc, &one, hmat, CUDA_R_32F,
-                                            (int)r, r * r, (int)bc, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT_TENSOR_OP));
+    // H_j (R x R) += sum_k s_k A_j[:,k] A_j[:,k]^T: own tcgen05 kernel (hmat_tc.cu), one CTA per image
+    if ((rc = launch_hmat_tc(x_a, svec, bc, r, kc, inv_ba, hmat, st))) return rc;
   }
   return 0;
 }
