@@ -463,8 +463,9 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       invZ = 1.f / (zb[widx] + zb[256 + widx]);
       k2 = p.g1 * kLog2e * invZ;
     };
-    if (j0 < j1) pass_a(0);
+    if (!BWD && j0 < j1) pass_a(0);
     for (int j = j0, it = 0; j < j1; ++j, ++it) {
+      if constexpr (BWD) pass_a(it);                                // backward: e1 stays live only until pass B
       const int b = it % nbuf;
       const uint32_t t_s = t_lane + (uint32_t)(b * L.tiles * NT);
       uint32_t e2p[NH / 2];
@@ -482,40 +483,35 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (warp == 1 && lane == 0) TRACE(p, 1, it, 1);
       // ---- pass B: e2 = exp(gamma1 P) (softmax over regions, un-normalised) -> fp16 B operand of GEMM2;
       //      forward also forms the N' = sum_r e2 S partial sums ----
-      auto pass_b = [&](auto width, auto cb) {
+      // B1 (critical path): e2 for every owned word -> fp16 -> the B operand of GEMM2, then GEMM2 can start.
+#pragma unroll
+      for (int tl = 0; tl < NH; tl += 2) {
+        if (DBG(p, 32)) break;
+        const float2 bz = tb22[tl >> 1];
+        const float a0 = ex2f(fmaf(e1[tl], k2, bz.x));
+        const float a1 = ex2f(fmaf(e1[tl + 1], k2, bz.y));
+        const uint32_t h2 = pack_half2(a0, a1) & rowmask;          // rows >= R contribute nothing
+        e2p[tl >> 1] = h2;
+        if (k_row) {
+          sts_u16(e2a[tl & 7] + tl * 128, h2 & 0xffffu);
+          sts_u16(e2a[(tl + 1) & 7] + (tl + 1) * 128, h2 >> 16);
+        }
+      }
+      // B2 (forward only, runs while GEMM2 is in flight): N' = sum_r e2 S partial sums
+      auto pass_b2 = [&](auto width, auto cb) {
         constexpr int W = decltype(width)::value;
         constexpr int cbeg = decltype(cb)::value;
         float x[W];
-        if constexpr (!BWD) tmem_ld<W>(t_s + cbeg, x);
+        tmem_ld<W>(t_s + cbeg, x);
 #pragma unroll
         for (int k = 0; k < W; k += 2) {
-          const int tl = cbeg + k;
-          const float2 bz = tb22[tl >> 1];
-          const float a0 = ex2f(fmaf(e1[tl], k2, bz.x));
-          const float a1 = ex2f(fmaf(e1[tl + 1], k2, bz.y));
-          const uint32_t h2 = pack_half2(a0, a1) & rowmask;        // rows >= R contribute nothing
-          e2p[tl >> 1] = h2;
-          if (k_row) {
-            sts_u16(e2a[tl & 7] + tl * 128, h2 & 0xffffu);
-            sts_u16(e2a[(tl + 1) & 7] + (tl + 1) * 128, h2 >> 16);
-          }
-          if constexpr (!BWD) {
-            const float2 f = unpack_half2(h2);                      // the values the tensor core will see
-            x[k] *= f.x;
-            x[k + 1] *= f.y;
-          }
+          const float2 f = unpack_half2(e2p[(cbeg + k) >> 1]);     // the values the tensor core sees
+          x[k] *= f.x;
+          x[k + 1] *= f.y;
         }
-        if constexpr (!BWD) {
-          const float cs = warp_colsum<W>(x, lane);
-          if (lane < W) red1w[(cbeg + lane) * 8] = cs;
-        }
+        const float cs = warp_colsum<W>(x, lane);
+        if (lane < W) red1w[(cbeg + lane) * 8] = cs;
       };
-      if (!DBG(p, 32)) {
-      if constexpr (NH >= 32) pass_b(std::integral_constant<int, 32>{}, std::integral_constant<int, 0>{});
-      if constexpr (NH == 64) pass_b(std::integral_constant<int, 32>{}, std::integral_constant<int, 32>{});
-      if constexpr (NH == 40) pass_b(std::integral_constant<int, 8>{}, std::integral_constant<int, 32>{});
-      if constexpr (NH == 16) pass_b(std::integral_constant<int, 16>{}, std::integral_constant<int, 0>{});
-      }
       // backward: the sweeps only need P = e1/Z to fp16 accuracy; halving its registers keeps them spill-free
       // (spills go to L2 here: the L1 is almost entirely carved out as shared memory)
       uint32_t e1h[BWD ? NH / 2 : 1];
@@ -524,11 +520,18 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int k = 0; k < NH / 2; ++k) e1h[k] = pack_half2(e1[2 * k] * invZ, e1[2 * k + 1] * invZ);
       }
       fence_proxy_async_smem();
-      tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(e2_ready);
-        if (!BWD) mbar_arrive(&s_free[b]);                          // forward: S is dead from here on
+      if (lane == 0) mbar_arrive(e2_ready);
+      if constexpr (!BWD) {
+        if (!DBG(p, 32)) {
+          if constexpr (NH >= 32) pass_b2(std::integral_constant<int, 32>{}, std::integral_constant<int, 0>{});
+          if constexpr (NH == 64) pass_b2(std::integral_constant<int, 32>{}, std::integral_constant<int, 32>{});
+          if constexpr (NH == 40) pass_b2(std::integral_constant<int, 8>{}, std::integral_constant<int, 32>{});
+          if constexpr (NH == 16) pass_b2(std::integral_constant<int, 16>{}, std::integral_constant<int, 0>{});
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[b]);                     // forward: S is dead from here on
       }
       if constexpr (BWD) {
         // ---- warp 0: per-word coefficients from the statistics the forward saved (rho, ||c||, 1/Y):
@@ -678,7 +681,6 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mbar_arrive(&s_free[b]);
           mbar_arrive(m_free);
         }
-        if (j + 1 < j1) pass_a(it + 1);
       }
     }
     if constexpr (!BWD) {
