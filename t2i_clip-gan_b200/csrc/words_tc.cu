@@ -465,7 +465,14 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     };
     if (!BWD && j0 < j1) pass_a(0);
     for (int j = j0, it = 0; j < j1; ++j, ++it) {
-      if constexpr (BWD) pass_a(it);                                // backward: e1 stays live only until pass B
+      if constexpr (BWD) {
+        // the per-pair statistics are streamed from HBM exactly once: start fetching the next pair's lines now
+        if (warp == 0 && j + 1 < j1 && lane < 8) {
+          const char *nx = reinterpret_cast<const char *>(p.stats + ((int64_t)i * p.bc + j + 1) * 3 * T) + lane * 128;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+        }
+        pass_a(it);                                                 // backward: e1 stays live only until pass B
+      }
       const int b = it % nbuf;
       const uint32_t t_s = t_lane + (uint32_t)(b * L.tiles * NT);
       uint32_t e2p[NH / 2];
