@@ -191,7 +191,7 @@ def main():
     args = ap.parse_args()
 
     pkg = importlib.import_module("t2i_clip-gan_b200")
-    has_tc = args.impl == "ours" and hasattr(pkg._lib.load(), "damsm_words_fwd_tc")
+    has_tc = hasattr(pkg._lib.load(), "damsm_words_fwd_tc")      # both arms measure the same workload
     if args.workload is None:
         args.workload = "c5" if has_tc else "c2"
     w = dict(WORKLOADS[args.workload])
@@ -362,15 +362,31 @@ def measure_roofline(pkg, w, dev, bl, B, rank, group, prec):
             return e0.elapsed_time(e1) / reps
 
         t_f = timed(lambda: eng.words_fwd(qhat, qhat16, vhat, col, qunorm, mask_u8, GAMMAS))
-        t_b = timed(lambda: eng.words_bwd(qhat, qhat16, vhat, col, qunorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
-                                          rank * bl, B, GAMMAS))
+        bwd = lambda: eng.words_bwd(qhat, qhat16, vhat, col, qunorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
+                                    rank * bl, B, GAMMAS)
+        t_b = timed(bwd)
+        t_b_fused = None
+        if prec == "bf16":      # the fused tcgen05 recompute kernel alone (library switch skips the gradient GEMMs)
+            os.environ["DAMSM_BWD_FUSED_ONLY"] = "1"
+            try:
+                t_b_fused = timed(bwd)
+            finally:
+                del os.environ["DAMSM_BWD_FUSED_ONLY"]
     f_fwd = 4.0 * bl * B * T * R * D
     f_bwd = 8.0 * bl * B * T * R * D
     ach = (f_fwd + f_bwd) / ((t_f + t_b) * 1e-3) / 1e12
+    # DRAM traffic of the two fused tcgen05 kernels per scored pair, from the committed ncu --set full capture
+    # (profiles/r1_ncu_tc_summary.md: forward 2.8 KB, backward 71.6 KB -- the fp16 dS/A scratch rows); fp32 path: none captured
+    traffic = (2.8e3 + 71.6e3) * bl * B if prec == "bf16" else None
     return dict(bound="tensor", achieved=ach, peak=peaks["bf16"], unit="TFLOP/s", frac=ach / peaks["bf16"],
-                traffic=None, peak_source=peaks["src"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
-                kernel="words pair kernels (fwd launch + bwd launch), algorithmic flops 4+8 * B_rows*B*T*R*D",
-                fwd_ms=t_f, bwd_ms=t_b, fwd_tflops=f_fwd / (t_f * 1e-3) / 1e12, bwd_tflops=f_bwd / (t_b * 1e-3) / 1e12,
+                traffic=traffic, traffic_note="bytes per step of the fused fwd+bwd kernels = ncu dram bytes per pair x pairs", peak_source=peaks["src"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
+                kernel=("word-loss operator: words_tc_kernel<FWD> (1 launch) + backward (words_tc_kernel<BWD> per chunk, "
+                        "hmat_tc_kernel, 2 cuBLAS GEMMs per chunk); algorithmic flops (4+8)*B_rows*B*T*R*D"
+                        if prec == "bf16" else
+                        "words_pair_f32_kernel fwd + bwd launches; algorithmic flops (4+8)*B_rows*B*T*R*D"),
+                fwd_ms=t_f, bwd_ms=t_b, bwd_fused_kernel_ms=t_b_fused,
+                bwd_gemms_ms=(t_b - t_b_fused) if t_b_fused is not None else None,
+                fwd_tflops=f_fwd / (t_f * 1e-3) / 1e12, bwd_tflops=f_bwd / (t_b * 1e-3) / 1e12,
                 note=("exact fp32 SIMT path: the tensor roofline is quoted for comparison only; this configuration is "
                       "latency-bound (SURVEY 8d)") if prec == "fp32" else "bf16 tcgen05 path")
 

@@ -941,6 +941,7 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
     p.x_ds = x_ds; p.x_a = x_a; p.svec = svec; p.scale_ds = scale_ds; p.scale_ba = scale_ba;
     p.dbg = getenv("DAMSM_DBG") ? atoi(getenv("DAMSM_DBG")) : 0;
     if ((rc = tc_launch<true>(tl, p, bi, st))) return rc;
+    if (getenv("DAMSM_BWD_FUSED_ONLY")) continue;   // bench.py times the fused recompute kernel alone this way
     if (getenv("DAMSM_DEBUG_SYNC")) {
       cudaError_t e = cudaStreamSynchronize(st);
       fprintf(stderr, "damsm debug: fused bwd kernel chunk i0=%lld done: %s\n", (long long)i0, cudaGetErrorString(e));

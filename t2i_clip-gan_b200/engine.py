@@ -156,6 +156,8 @@ class CudaEngine:
                   _lib.ptr(labels), gscale.data_ptr(), int(row_offset), int(b_total), br, bc, t, r, d,
                   float(gammas[0]), float(gammas[1]), float(gammas[2]), ws.data_ptr(), ws_bytes,
                   dqhat.data_ptr(), dvhat.data_ptr(), hmat.data_ptr(), kq.data_ptr(), _stream())
+        chunks = -(-br // max(1, ws_bytes // row_bytes))
+        _lib.add_launches(2 * chunks - 1)          # own kernels per chunk: fused recompute + hmat (cuBLAS not counted)
         _lib.call("damsm_gram_bwd_f32", hmat.data_ptr(), vhat.data_ptr(), bc, r, d, dvhat.data_ptr(), _stream())
         return dqhat[:, :t, :], dvhat, kq
 
