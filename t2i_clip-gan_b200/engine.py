@@ -74,25 +74,40 @@ class CudaEngine:
         return dx
 
     # ---- word / region scores ---------------------------------------------------------------------------
-    def words_prepare_columns(self, vhat: torch.Tensor, vhat16=None):
-        """Per-image side data derived from vhat (bc,R,D): the Gram matrices (fp32) and, for the
-        tensor-core path, their padded bf16 form with the appended row of ones."""
+    def gram(self, vhat: torch.Tensor):
+        """Per-image Gram matrices G_j = vhat_j vhat_j^T (bc,R,R) fp32 of the LOCAL images."""
         bc, r, d = vhat.shape
         gram = torch.empty((bc, r, r), device=vhat.device, dtype=torch.float32)
         _lib.call("damsm_gram_f32", vhat.data_ptr(), bc, r, d, gram.data_ptr(), _stream())
+        return gram
+
+    def pack_columns(self, gram: torch.Tensor, vhat, vhat16=None):
+        """Image-side operands of the pair kernels from the (gathered) Gram matrices and normalised regions:
+        fp32 path: gram + vhat; tensor-core path: the padded fp16 Gram form with the appended row of ones + vhat16."""
         col = {"gram": gram}
         if self.precision == "bf16":
+            bc, r, _ = gram.shape
             rk = _lib.load().damsm_words_tc_gx_cols(r)
-            gx = torch.empty((bc, r + 1, rk), device=vhat.device, dtype=torch.float16)
+            gx = torch.empty((bc, r + 1, rk), device=gram.device, dtype=torch.float16)
             _lib.call("damsm_gram_pack_tc", gram.data_ptr(), bc, r, gx.data_ptr(), _stream())
             col["gx"] = gx
             col["vhat16"] = vhat16
         return col
 
+    def words_prepare_columns(self, vhat: torch.Tensor, vhat16=None):
+        """Single-GPU convenience: gram + pack_columns."""
+        return self.pack_columns(self.gram(vhat), vhat, vhat16)
+
+    def gram_bwd(self, hmat, vhat, dvhat):
+        """dvhat_j -= H_j vhat_j (in place) for the LOCAL images, after H and dvhat have been reduced over ranks."""
+        bc, r, d = vhat.shape
+        _lib.call("damsm_gram_bwd_f32", hmat.data_ptr(), vhat.data_ptr(), bc, r, d, dvhat.data_ptr(), _stream())
+        return dvhat
+
     def words_fwd(self, qhat, qhat16, vhat, col, unorm, mask_u8, gammas, want_stats=True):
-        _require_cuda(qhat, vhat, unorm, mask_u8)
+        _require_cuda(qhat, unorm, mask_u8)
         br, t, d = qhat.shape
-        bc, r, _ = vhat.shape
+        bc, r, _ = col["gram"].shape
         sim = torch.empty((br, bc), device=qhat.device, dtype=torch.float32)
         if self.precision == "bf16":
             # per-pair, per-word scalars (rho, ||c||, 1/Y) for the backward: 12*T bytes per pair
@@ -111,13 +126,15 @@ class CudaEngine:
 
     def words_bwd(self, qhat, qhat16, vhat, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
                   row_offset, b_total, gammas):
-        """Returns (dqhat (br,T,D), dvhat (bc,R,D) partial over this rank's rows, kq (br,T))."""
+        """Returns (dqhat (br,T,D), dvhat (bc,R,D), hmat (bc,R,R), kq (br,T)); dvhat and hmat are partial sums over
+        this rank's caption rows and dvhat does not yet contain the -H vhat term (see gram_bwd).  ``vhat`` is only
+        read by the fp32 path."""
         gram = col["gram"]
         br, t, d = qhat.shape
-        bc, r, _ = vhat.shape
+        bc, r, _ = gram.shape
         dev = qhat.device
         if self.precision == "bf16":
-            return self._words_bwd_tc(qhat16, vhat, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
+            return self._words_bwd_tc(qhat16, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
                                       row_offset, b_total, gammas, br, bc, t, r, d)
         dqhat = torch.zeros((br, t, d), device=dev, dtype=torch.float32)
         dvhat = torch.zeros((bc, r, d), device=dev, dtype=torch.float32)
@@ -128,16 +145,15 @@ class CudaEngine:
                   gscale.data_ptr(), int(row_offset), int(b_total), br, bc, t, r, d,
                   float(gammas[0]), float(gammas[1]), float(gammas[2]),
                   dqhat.data_ptr(), dvhat.data_ptr(), hmat.data_ptr(), kq.data_ptr(), _stream())
-        _lib.call("damsm_gram_bwd_f32", hmat.data_ptr(), vhat.data_ptr(), bc, r, d, dvhat.data_ptr(), _stream())
-        return dqhat, dvhat, kq
+        return dqhat, dvhat, hmat, kq
 
     # scratch for the tensor-core backward: the fused kernel + GEMMs run chunk by chunk inside it.  Larger chunks
     # mean fewer launches and a longer K for the gradient GEMMs; default = a third of the free HBM, at least 6 GiB.
     tc_workspace_bytes = None
 
-    def _words_bwd_tc(self, qhat16, vhat, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
+    def _words_bwd_tc(self, qhat16, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
                       row_offset, b_total, gammas, br, bc, t, r, d):
-        dev = vhat.device
+        dev = qhat16.device
         tp = qhat16.shape[1]
         lib = _lib.load()
         row_bytes = lib.damsm_words_bwd_tc_row_bytes(bc, t, r)
@@ -158,8 +174,7 @@ class CudaEngine:
                   dqhat.data_ptr(), dvhat.data_ptr(), hmat.data_ptr(), kq.data_ptr(), _stream())
         chunks = -(-br // max(1, ws_bytes // row_bytes))
         _lib.add_launches(2 * chunks - 1)          # own kernels per chunk: fused recompute + hmat (cuBLAS not counted)
-        _lib.call("damsm_gram_bwd_f32", hmat.data_ptr(), vhat.data_ptr(), bc, r, d, dvhat.data_ptr(), _stream())
-        return dqhat[:, :t, :], dvhat, kq
+        return dqhat[:, :t, :], dvhat, hmat, kq
 
     # ---- masked bidirectional cross-entropy ---------------------------------------------------------------
     def ce_stats(self, logits, cls_rows, cls_cols, row_offset):

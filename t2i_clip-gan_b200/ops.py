@@ -79,10 +79,14 @@ class DamsmWordsLoss(torch.autograd.Function):
         b_total, row_offset = bl * world, rank * bl
         qhat, qhat16, qnorm, qunorm = engine.l2norm_fwd(words3, want_bf16=engine.precision == "bf16", pad8=True)
         vhat_l, vhat16_l, vnorm, _ = engine.l2norm_fwd(regions3, want_bf16=engine.precision == "bf16")
-        vhat = _all_gather_rows(vhat_l, group)
+        # image side: Gram matrices are computed for the local images only and gathered with the operands the
+        # pair kernels read (fp32 path: vhat; tensor-core path: the fp16 copy)
+        gram = _all_gather_rows(engine.gram(vhat_l), group)
+        tc = engine.precision == "bf16"
+        vhat = vhat_l if (group is None or tc) else _all_gather_rows(vhat_l, group)
         vhat16 = _all_gather_rows(vhat16_l, group) if vhat16_l is not None else None
         cls_all = _all_gather_rows(cls_local, group) if cls_local is not None else None
-        colside = engine.words_prepare_columns(vhat, vhat16)
+        colside = engine.pack_columns(gram, vhat, vhat16)
         sim = engine.words_fwd(qhat, qhat16, vhat, colside, qunorm, mask_u8, gammas)
         row_lse, col_max, col_sum = engine.ce_stats(sim, cls_local, cls_all, row_offset)
         col_lse = combine_column_lse(col_max, col_sum, group)
@@ -92,22 +96,25 @@ class DamsmWordsLoss(torch.autograd.Function):
         ctx.engine, ctx.group, ctx.gammas = engine, group, gammas
         ctx.row_offset, ctx.b_total = row_offset, b_total
         ctx.colside, ctx.qhat16 = colside, qhat16
-        ctx.save_for_backward(regions3, words3, mask_u8, labels, qhat, vhat, qnorm, qunorm, vnorm,
+        ctx.save_for_backward(regions3, words3, mask_u8, labels, qhat, vhat, vhat_l, qnorm, qunorm, vnorm,
                               sim, row_lse, col_lse)
         ctx.mark_non_differentiable(sim)
         return out2[0].clone(), out2[1].clone(), sim
 
     @staticmethod
     def backward(ctx, g0, g1, _gsim):
-        (regions3, words3, mask_u8, labels, qhat, vhat, qnorm, qunorm, vnorm,
+        (regions3, words3, mask_u8, labels, qhat, vhat, vhat_l, qnorm, qunorm, vnorm,
          sim, row_lse, col_lse) = ctx.saved_tensors
         eng, colside = ctx.engine, ctx.colside
         gscale = torch.stack([g0.reshape(()), g1.reshape(())]).to(torch.float32)
-        dqhat, dvhat, kq = eng.words_bwd(qhat, ctx.qhat16, vhat, colside, qunorm, mask_u8, sim, row_lse, col_lse, labels,
-                                         gscale, ctx.row_offset, ctx.b_total, ctx.gammas)
+        dqhat, dvhat, hmat, kq = eng.words_bwd(qhat, ctx.qhat16, vhat, colside, qunorm, mask_u8, sim, row_lse, col_lse,
+                                               labels, gscale, ctx.row_offset, ctx.b_total, ctx.gammas)
         dregions3 = dwords3 = None
         if ctx.needs_input_grad[0]:
+            # partial sums over this rank's captions for ALL images -> owners; the -H vhat term is applied there
             dvhat_l = _reduce_scatter_rows(dvhat, ctx.group)
+            hmat_l = _reduce_scatter_rows(hmat, ctx.group)
+            dvhat_l = eng.gram_bwd(hmat_l, vhat_l, dvhat_l)
             dregions3 = eng.l2norm_bwd(regions3, vnorm, dvhat_l, None)
         if ctx.needs_input_grad[1]:
             dwords3 = eng.l2norm_bwd(words3, qnorm, dqhat, kq)

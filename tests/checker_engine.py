@@ -38,9 +38,18 @@ class CheckerEngine:
             g = g - _np(kq)[..., None] * xhat / u2
         return _t(O.l2norm_bwd(x, nrm, g), x3.dtype)
 
-    def words_prepare_columns(self, vhat, vhat16=None):
+    def gram(self, vhat):
         v = _np(vhat)
-        return {"gram": np.einsum("jrd,jsd->jrs", v, v)}
+        return _t(np.einsum("jrd,jsd->jrs", v, v), torch.float64)
+
+    def pack_columns(self, gram, vhat, vhat16=None):
+        return {"gram": _np(gram)}
+
+    def words_prepare_columns(self, vhat, vhat16=None):
+        return self.pack_columns(self.gram(vhat), vhat, vhat16)
+
+    def gram_bwd(self, hmat, vhat, dvhat):
+        return _t(_np(dvhat) - np.einsum("jrs,jsd->jrd", _np(hmat), _np(vhat)), torch.float64)
 
     def _blocks(self, qhat, vhat, col, unorm, mask_u8, gammas):
         q, v, u, m = _np(qhat), _np(vhat), _np(unorm), _np(mask_u8)
@@ -103,8 +112,7 @@ class CheckerEngine:
             kq[i] = (beta * k["rho"]).sum(axis=0)
             dv += np.einsum("jtr,td->jrd", dS, q[i])
             H += np.einsum("jt,jtr,jts->jrs", b, A, A)
-        dv -= np.einsum("jrs,jsd->jrd", H, v)
-        return _t(dq, torch.float64), _t(dv, torch.float64), _t(kq, torch.float64)
+        return _t(dq, torch.float64), _t(dv, torch.float64), _t(H, torch.float64), _t(kq, torch.float64)
 
     def cos_logits(self, a, b, gamma3, eps):
         A, B = _np(a), _np(b)
