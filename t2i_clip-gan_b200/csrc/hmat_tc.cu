@@ -14,7 +14,7 @@ namespace damsm {
 using namespace tc;
 
 constexpr int HM_THREADS = 320;   // warps 0-7: scale + epilogue, 8: TMA producer, 9: MMA issuer
-constexpr int HM_SA = 3;          // TMA stages of A
+constexpr int HM_SA = 5;          // TMA stages of A (the ring must cover ~2.5k cycles of TMA + commit latency)
 constexpr int HM_SB = 2;          // scaled-copy buffers
 
 struct HmatParams {

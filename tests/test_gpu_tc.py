@@ -27,7 +27,8 @@ def rounded(x):
 
 
 @pytest.mark.parametrize("B,T,R,seed", [(6, 5, 9, 1), (12, 18, 49, 2), (9, 28, 49, 3), (5, 77, 49, 4), (4, 77, 196, 5),
-                                        (7, 40, 120, 6), (3, 64, 127, 7), (20, 18, 196, 8)])
+                                        (7, 40, 120, 6), (3, 64, 127, 7), (20, 18, 196, 8), (4, 30, 250, 9),
+                                        (3, 128, 64, 10)])
 def test_tc_forward_scores(B, T, R, seed):
     """sim matrix (before masking / CE) of the tcgen05 kernel vs the exact fp32 kernel and the oracle."""
     x = rounded(O.make_inputs(B, T, R, seed=seed, class_ids=False))
@@ -47,7 +48,10 @@ def test_tc_forward_scores(B, T, R, seed):
     assert err <= TOL, err
 
 
-@pytest.mark.parametrize("B,T,R,cls,seed", [(8, 18, 49, True, 11), (6, 77, 196, False, 12), (16, 28, 49, True, 13)])
+@pytest.mark.parametrize("B,T,R,cls,seed", [(8, 18, 49, True, 11), (6, 77, 196, False, 12), (16, 28, 49, True, 13),
+                                            (5, 18, 250, False, 14),      # R+1 > 224: 18-warp kernel variant
+                                            (4, 100, 49, True, 15),       # T > 80: NT = 128
+                                            (3, 7, 16, False, 16)])
 def test_tc_words_loss_and_grads(B, T, R, cls, seed):
     x = rounded(O.make_inputs(B, T, R, seed=seed, class_ids=cls, n_classes=4))
     o = O.words_loss(x["words"], x["regions"], x["mask"], x["labels"], x["class_ids"], 4.0, 5.0, 10.0)
