@@ -37,6 +37,9 @@ WORKLOADS = {
     "c3": dict(B=10, T=77, R=49, cls=True, precision="fp32", seed=2028, desc="DM-GAN generator-step DAMSM term"),
     "c4": dict(B=1024, T=77, R=196, cls=False, precision="bf16", seed=2029, desc="large-batch fine-tune, ViT-B/16"),
     "c5": dict(B=4096, T=77, R=196, cls=False, precision="bf16", seed=2030, desc="scaling sweep, ViT-B/16, bf16 in"),
+    # the NT-Xent term of the same training loss (nt_xent.py), its own metric
+    "ntx48": dict(B=48, ntxent=True, temperature=0.5, seed=2031, desc="NT-Xent, pretrain batch (pretrain_DAMSM.py:445-449)"),
+    "ntx4096": dict(B=4096, ntxent=True, temperature=0.5, seed=2032, desc="NT-Xent at the scaling-sweep batch"),
 }
 
 
@@ -178,6 +181,111 @@ def run_reference(args, w):
     print(json.dumps(line))
 
 
+# --------------------------------------------------------------------------------------------- NT-Xent (8f-1)
+def ntxent_inputs(w):
+    g = torch.Generator().manual_seed(w["seed"])
+    s = torch.randn(w["B"], D, generator=g)
+    return (0.25 * s + torch.randn(w["B"], D, generator=g)), (0.25 * s + torch.randn(w["B"], D, generator=g))
+
+
+def ntxent_cpu(w, steps, budget_s=20.0):
+    """The reference procedure (oracle/ref_port.ntxent_step) on the host cores; the (2B,2B,D) broadcast bounds B."""
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = w["B"]
+    Bs = min(B, 64)
+    zi, zj = ntxent_inputs(dict(w, B=Bs))
+    ref_port.ntxent_step(zi.numpy(), zj.numpy(), w["temperature"])
+    ts = []
+    t_end = time.perf_counter() + budget_s
+    while len(ts) < steps and (time.perf_counter() < t_end or len(ts) < 2):
+        t0 = time.perf_counter()
+        ref_port.ntxent_step(zi.numpy(), zj.numpy(), w["temperature"])
+        ts.append(time.perf_counter() - t0)
+    t_sample = float(np.median(ts))
+    t_full = t_sample * (B / Bs) ** 2
+    return dict(value=2 * B / t_full, unit="embedding rows/s", cores=cores, kind="port",
+                sample=(f"B={Bs} (2B={2 * Bs} rows, D={D}, fp32) fwd+bwd, median of {len(ts)}; "
+                        + ("full size" if Bs == B else f"extrapolated to B={B} with time ~ B^2")),
+                measured_ms_per_sample_step=t_sample * 1e3, sample_batch=Bs), t_full
+
+
+def run_ntxent(args, w):
+    """One step = NT_Xent(z_i, z_j) forward + backward (gradients to both codes); value = rows of cat(z_i, z_j) per s."""
+    B = w["B"]
+    cfgd = dict(workload=args.workload, description=w["desc"], B=B, D=D, temperature=w["temperature"])
+    if args.impl == "reference":
+        base, t_full = ntxent_cpu(w, args.steps)
+        print(json.dumps(dict(metric="nt_xent_fwd_bwd_rows_per_s", value=base["value"], unit="embedding rows/s",
+                              impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                              ms_per_step=t_full * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None,
+                              dtype="f32", data="synthetic", config=cfgd, cpu_baseline=base,
+                              e2e=dict(value=base["value"], unit="embedding rows/s", h2d_bytes_per_step=0,
+                                       d2h_bytes_per_step=0))))
+        return
+    pkg = importlib.import_module("t2i_clip-gan_b200")
+    torch.cuda.set_device(0)
+    zi_h, zj_h = (t.contiguous().pin_memory() for t in ntxent_inputs(w))
+
+    def step(zi, zj):
+        loss = pkg.nt_xent(zi, zj, w["temperature"])
+        loss.backward()
+        return loss.detach()
+
+    zi = zi_h.cuda().requires_grad_(True)
+    zj = zj_h.cuda().requires_grad_(True)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for _ in range(args.warmup):
+        zi.grad = zj.grad = None
+        step(zi, zj)
+    torch.cuda.synchronize()
+    pkg._lib.reset_launch_count()
+    sampler = ClockSampler(0)
+    evs = []
+    for _ in range(args.steps):
+        zi.grad = zj.grad = None
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = step(zi, zj)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    launches = pkg._lib.launch_count()
+    clocks = sampler.stop()
+    ms_step = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    out_pinned = torch.empty(1, dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        step(zi_h.to("cuda", non_blocking=True).requires_grad_(True), zj_h.to("cuda", non_blocking=True).requires_grad_(True))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        a = zi_h.to("cuda", non_blocking=True).requires_grad_(True)
+        b = zj_h.to("cuda", non_blocking=True).requires_grad_(True)
+        out_pinned.copy_(step(a, b).reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    peaks = load_peaks()
+    n2 = 2 * B
+    # algorithmic HBM bytes: read z in forward and backward, write dz (the 2B x 2B logits are an intermediate)
+    alg_bytes = 3.0 * n2 * D * 4
+    roof = dict(bound="hbm", achieved=alg_bytes / (ms_step * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
+                frac=alg_bytes / (ms_step * 1e-3) / 1e9 / peaks["hbm"], traffic=None, peak_source=peaks["src"],
+                note=("latency-bound: 7 small launches; the exact-fp32 SIMT GEMMs (6*(2B)^2*D flop fwd+bwd = "
+                      f"{6.0 * n2 * n2 * D / 1e9:.2f} GFLOP) and the 2B x 2B fp32 logits dominate at large B"))
+    base = None if args.no_cpu_baseline else ntxent_cpu(w, 5)[0]
+    print(json.dumps(dict(metric="nt_xent_fwd_bwd_rows_per_s", value=n2 / (ms_step * 1e-3), unit="embedding rows/s",
+                          n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True,
+                          scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
+                          config=dict(cfgd, l2="L2 flushed (256 MiB memset) between timed iterations",
+                                      step="NT_Xent forward + backward, grads to both codes"),
+                          loss=float(loss.item()), clocks=clocks,
+                          e2e=dict(value=n2 / e2e_s, unit="embedding rows/s", ms_per_step=e2e_s * 1e3,
+                                   h2d_bytes_per_step=int(2 * B * D * 4), d2h_bytes_per_step=4),
+                          gpu_launches=launches, roofline=roof, cpu_baseline=base)))
+
+
 # --------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -200,6 +308,10 @@ def main():
     if args.steps is None:
         args.steps = 5 if w["B"] >= 1024 else 20
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if w.get("ntxent"):
+        if int(os.environ.get("RANK", "0")) == 0:      # replicas only: the term is O(B^2 D), not sharded
+            run_ntxent(args, w)
+        return
 
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) == 0:

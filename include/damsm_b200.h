@@ -156,6 +156,17 @@ DAMSM_API int damsm_cos_logits_bwd_f32(const float *a, int64_t lda, const float 
                              int64_t br, int64_t bc, int64_t d, float gamma3, float eps,
                              float *work, float *da, float *db, void *stream);
 
+/* ---- NT-Xent contrastive term (nt_xent.py:16-35 with the mask of masks.py:3-17; used at
+ * pretrain_DAMSM.py:170-174 and trainer.py:417-430).  z (n2,d) = cat(z_i, z_j), rows ldz floats apart, n2 = 2B.
+ * sim (n2,n2) out: cosine / temperature, -inf on the diagonal; nrm (n2) = |z_a|; row_lse (n2);
+ * loss[0] = 1/n2 sum_a (LSE_{b!=a} sim[a][b] - sim[a][(a+B) mod n2]).  eps clamps each norm (CosineSimilarity). */
+DAMSM_API int damsm_ntxent_fwd_f32(const float *z, int64_t ldz, int64_t n2, int64_t d, float inv_temp, float eps,
+                         float *sim, float *nrm, float *row_lse, float *loss, void *stream);
+/* gout: device scalar dL/dloss; work: scratch of n2*n2 + n2 floats; dz (n2,d) contiguous is OVERWRITTEN */
+DAMSM_API int damsm_ntxent_bwd_f32(const float *z, int64_t ldz, int64_t n2, int64_t d, float inv_temp, float eps,
+                         const float *sim, const float *nrm, const float *row_lse, const float *gout,
+                         float *work, float *dz, void *stream);
+
 /* ---- func_attention (GlobalAttention.py:38-160): one (caption b, image b) pair per batch element -------
  * wc (B,T,D) = A . context_RAW (line :153), attn (B,T,R) = softmax over words (line :104),
  * attn2 (B,T,R) = softmax over regions of gamma1*attn (saved for backward).

@@ -239,6 +239,40 @@ def sent_loss(img, txt, labels, class_ids, gamma3, g0=1.0, g1=1.0):
     return dict(loss0=loss0, loss1=loss1, scores=scm, dimg=dimg, dtxt=dtxt)
 
 
+# --------------------------------------------------------------------------- NT-Xent
+NTX_EPS = 1e-8   # nn.CosineSimilarity default eps (nt_xent.py:14), clamps each norm
+
+
+def nt_xent(z_i, z_j, temperature, g=1.0):
+    """nt_xent.py:16-35 with the mask of masks.py:3-17.
+
+    z = cat(z_i, z_j); sim = cos(z_a, z_b) / temperature (:23-24); positives on the +-B diagonals (:26-29);
+    negatives = everything but the diagonal and the positive (:30, masks.py); logits = [positive, negatives],
+    label 0, CrossEntropy(sum) / 2B (:32-35)  ==  mean_a( LSE_{b != a} sim[a, b] - sim[a, pos(a)] ).
+    Returns dict(loss, sim (diag = -inf), dz_i, dz_j) with the analytic gradient of g * loss."""
+    z = np.concatenate([np.asarray(z_i, np.float64), np.asarray(z_j, np.float64)], axis=0)
+    n2 = z.shape[0]
+    b = n2 // 2
+    nr = np.sqrt((z * z).sum(-1))
+    cn = np.maximum(nr, NTX_EPS)
+    sim = (z @ z.T) / (cn[:, None] * cn[None, :]) / temperature
+    np.fill_diagonal(sim, -np.inf)
+    pos = (np.arange(n2) + b) % n2
+    mx = sim.max(axis=1, keepdims=True)
+    lse = np.log(np.exp(sim - mx).sum(axis=1)) + mx[:, 0]
+    loss = float((lse - sim[np.arange(n2), pos]).mean())
+    gm = np.exp(sim - lse[:, None])                           # softmax over b != a (exp(-inf) = 0 on the diagonal)
+    gm[np.arange(n2), pos] -= 1.0
+    gm *= g / n2                                              # dL/dsim
+    w = gm / temperature / (cn[:, None] * cn[None, :])        # dL/d(z_a . z_b)
+    sfin = np.where(np.isfinite(sim), sim, 0.0)
+    live = nr > NTX_EPS
+    coef = np.where(live, -(gm * sfin).sum(1) / np.where(live, nr, 1.0), 0.0) \
+        + np.where(live, -(gm * sfin).sum(0) / np.where(live, nr, 1.0), 0.0)      # dL/d|z_x| via row x and column x
+    dz = (w + w.T) @ z + coef[:, None] * z / np.where(nr > 0, nr, 1.0)[:, None]
+    return dict(loss=loss, sim=sim, dz_i=dz[:b], dz_j=dz[b:])
+
+
 # --------------------------------------------------------------------------- func_attention
 def func_attention(query, context, gamma1, query_mask, d_wc=None):
     """GlobalAttention.py:38-160.

@@ -38,6 +38,8 @@ CASES = {
 }
 
 
+NTX_TEMPERATURE = 0.5                     # pretrain_DAMSM.py:447, trainer.py:288
+
 SAMPLE_STRIDE = 61   # gradients / maps are stored as a strided sample + full-tensor norms
 
 
@@ -76,6 +78,11 @@ def main():
         for key, arr in (("dwords", w["dwords"]), ("dregions", w["dregions"]), ("attn0", w["attn0"]),
                          ("dimg", s["dimg"]), ("dtxt", s["dtxt"])):
             pack(rec, key, arr)
+        nx = RS.ref_nt_xent(x["sent"], x["img"], NTX_TEMPERATURE)       # as pretrain_DAMSM.py:170-174: two (B, D) codes
+        rec["ntx_loss"] = np.float32(nx["loss"])
+        rec["ntx_temperature"] = np.float64(NTX_TEMPERATURE)
+        pack(rec, "ntx_dzi", nx["dz_i"])
+        pack(rec, "ntx_dzj", nx["dz_j"])
         if int(np.sqrt(R)) ** 2 == R:
             rng = np.random.default_rng(seed + 1000)
             dwc = rng.standard_normal((B, T, 512)).astype(np.float32)

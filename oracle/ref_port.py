@@ -110,3 +110,22 @@ def step(x, gammas=(4.0, 5.0, 10.0), checks=True):
     (w0 + w1 + s0 + s1).backward()
     return dict(w_loss0=w0.item(), w_loss1=w1.item(), s_loss0=s0.item(), s_loss1=s1.item(),
                 dwords=w.grad.numpy(), dregions=r.grad.numpy(), dimg=si.grad.numpy(), dtxt=st.grad.numpy())
+
+
+def ntxent_step(z_i, z_j, temperature):
+    """NT_Xent.forward + backward the way the reference runs it (nt_xent.py:16-35): the (2B, 2B, D) broadcast
+    cosine (:24), positives from the +-B diagonals (:26-29), negatives through the boolean mask of masks.py (:30),
+    CrossEntropy(sum) / 2B (:32-35).  Returns dict(loss, dz_i, dz_j)."""
+    a = torch.tensor(np.asarray(z_i), dtype=torch.float32, requires_grad=True)
+    b = torch.tensor(np.asarray(z_j), dtype=torch.float32, requires_grad=True)
+    bsz = a.shape[0]
+    n2 = 2 * bsz
+    p = torch.cat((a, b), dim=0)
+    sim = torch.nn.functional.cosine_similarity(p.unsqueeze(1), p.unsqueeze(0), dim=2) / temperature
+    positives = torch.cat((sim.diagonal(bsz), sim.diagonal(-bsz))).reshape(n2, 1)
+    idx = torch.arange(n2)
+    keep = (idx[:, None] != idx[None, :]) & ((idx[:, None] - idx[None, :]).abs() != bsz)
+    logits = torch.cat((positives, sim[keep].reshape(n2, -1)), dim=1)
+    loss = torch.nn.functional.cross_entropy(logits, torch.zeros(n2, dtype=torch.long), reduction="sum") / n2
+    loss.backward()
+    return dict(loss=float(loss.detach()), dz_i=a.grad.numpy().copy(), dz_j=b.grad.numpy().copy())

@@ -4,7 +4,7 @@ Used by ``oracle/make_golden.py`` (to record golden vectors) and by
 ``tests/test_oracle_vs_reference.py`` (live comparison, skipped where
 ``/root/reference`` does not exist, e.g. on the GPU box).  Nothing under
 ``/root/reference`` is modified or copied; this file only arranges for
-``miscc/losses.py`` and ``GlobalAttention.py`` to import:
+``miscc/losses.py``, ``GlobalAttention.py`` (and ``nt_xent.py`` / ``masks.py``) to import:
 
   * ``easydict`` is not installed -> an in-memory stand-in module
     (needed by miscc/config.py:6);
@@ -145,3 +145,25 @@ def ref_func_attention(query_btd, context_brd, gamma1, query_mask, d_wc=None):
             out["dquery"] = q.grad.numpy().copy()
             out["dcontext"] = c.grad.numpy().copy()
     return out
+
+
+def ref_nt_xent(z_i, z_j, temperature):
+    """Run the reference NT_Xent (nt_xent.py:4-35) with its own mask builder (masks.py:11-17), fp32.
+    Returns dict(loss, dz_i, dz_j).  The two files are loaded under private module names."""
+    import importlib.util
+    import numpy as np
+    import torch
+    mods = []
+    for name in ("nt_xent", "masks"):
+        spec = importlib.util.spec_from_file_location("_ref_" + name, os.path.join(REF_ROOT, name + ".py"))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        mods.append(m)
+    ntx, masks = mods
+    a = torch.tensor(np.asarray(z_i), dtype=torch.float32, requires_grad=True)
+    b = torch.tensor(np.asarray(z_j), dtype=torch.float32, requires_grad=True)
+    B = a.shape[0]
+    crit = ntx.NT_Xent(B, float(temperature), masks.mask_correlated_samples_2(B), torch.device("cpu"))
+    loss = crit(a, b)
+    loss.backward()
+    return dict(loss=float(loss.detach()), dz_i=a.grad.numpy().copy(), dz_j=b.grad.numpy().copy())

@@ -83,6 +83,81 @@ __global__ void __launch_bounds__(256) norm_term_kernel(float *__restrict__ gx, 
   if (nr > 0.f) gx[e] += coef[row] * x[(int64_t)row * ld + k] / nr;
 }
 
+
+// ------------------------------------------------------------------------------------------- NT-Xent (nt_xent.py:16-35)
+// z = cat(z_i, z_j) (n2 = 2B rows); sim[a][b] = z_a.z_b / (max(|z_a|,eps) max(|z_b|,eps)) / temperature
+// (nn.CosineSimilarity clamps EACH norm, nt_xent.py:14,24); positives sit on the +-B diagonals (:26-27), the mask
+// (masks.py:3-17) removes the diagonal and the positives from the negatives, so
+//   loss = 1/n2 sum_a ( LSE_{b != a} sim[a][b] - sim[a][(a + B) mod n2] )         (CrossEntropy(sum) / 2B, :33-34).
+// The reference materialises an n2 x n2 x D broadcast (:24); here: one SIMT GEMM + one row kernel.
+// One CTA per row: scale the dot products in place, put -inf on the diagonal, row LSE, loss contribution.
+__global__ void __launch_bounds__(256) ntxent_row_kernel(float *__restrict__ sim, const float *__restrict__ nrm, int n2,
+                                                         float inv_temp, float eps, float *__restrict__ row_lse,
+                                                         float *__restrict__ loss) {
+  const int a = blockIdx.x;
+  float *row = sim + (int64_t)a * n2;
+  const float ia = inv_temp / fmaxf(nrm[a], eps);
+  float mx = -INFINITY;
+  for (int b = threadIdx.x; b < n2; b += blockDim.x) {
+    const float s = (b == a) ? -INFINITY : row[b] * ia / fmaxf(nrm[b], eps);
+    row[b] = s;
+    mx = fmaxf(mx, s);
+  }
+  __shared__ float red[8];
+  __shared__ float bc;
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    bc = m;
+  }
+  __syncthreads();
+  mx = bc;
+  float se = 0.f;
+  for (int b = threadIdx.x; b < n2; b += blockDim.x) se += expf(row[b] - mx);     // own writes; exp(-inf) = 0
+  se = warp_sum(se);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = se;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    const float lse = logf(t) + mx;
+    row_lse[a] = lse;
+    const int pos = (a + n2 / 2) % n2;
+    atomicAdd(loss, (lse - row[pos]) / (float)n2);
+  }
+}
+
+// work[a][b] = dL/d(z_a.z_b) = g_ab inv_temp / (n_a n_b),  g_ab = gout/n2 (softmax_row(sim)_ab - [b == pos(a)]);
+// coef[x] = dL/d|z_x| through both roles of z_x (row a and column b) where its clamp is inactive.
+__global__ void __launch_bounds__(256) ntxent_bwd_coef_kernel(const float *__restrict__ sim, const float *__restrict__ nrm,
+                                                              const float *__restrict__ row_lse,
+                                                              const float *__restrict__ gout, int n2, float inv_temp,
+                                                              float eps, float *__restrict__ work,
+                                                              float *__restrict__ coef) {
+  const int a = blockIdx.x;
+  const float na = nrm[a], ca = fmaxf(na, eps), lse = row_lse[a], gs = gout[0] / (float)n2;
+  const int pos = (a + n2 / 2) % n2;
+  float racc = 0.f;
+  for (int b = threadIdx.x; b < n2; b += blockDim.x) {
+    const float s = sim[(int64_t)a * n2 + b];
+    float w = 0.f;
+    if (b != a) {
+      const float g = gs * (expf(s - lse) - (b == pos ? 1.f : 0.f));
+      const float nb = nrm[b], cb = fmaxf(nb, eps);
+      w = g * inv_temp / (ca * cb);
+      if (na > eps) racc = fmaf(-g, s / na, racc);
+      if (nb > eps) atomicAdd(coef + b, -g * s / nb);
+    }
+    work[(int64_t)a * n2 + b] = w;
+  }
+  racc = warp_sum(racc);
+  if ((threadIdx.x & 31) == 0 && racc != 0.f) atomicAdd(coef + a, racc);
+}
+
 }  // namespace damsm
 
 using namespace damsm;
@@ -141,4 +216,48 @@ extern "C" int damsm_cos_logits_bwd_f32(const float *a, int64_t lda, const float
   norm_term_kernel<<<(unsigned)((br * d + 255) / 256), 256, 0, st>>>(da, a, lda, rowc, na, (int)br, (int)d);
   norm_term_kernel<<<(unsigned)((bc * d + 255) / 256), 256, 0, st>>>(db, b, ldb, colc, nb, (int)bc, (int)d);
   return check_launch("cos_logits_bwd");
+}
+
+extern "C" int damsm_ntxent_fwd_f32(const float *z, int64_t ldz, int64_t n2, int64_t d, float inv_temp, float eps,
+                                    float *sim, float *nrm, float *row_lse, float *loss, void *stream) {
+  DAMSM_REQUIRE(z && sim && nrm && row_lse && loss, "ntxent_fwd: null pointer");
+  DAMSM_REQUIRE(n2 >= 2 && n2 % 2 == 0 && d > 0 && ldz >= d, "ntxent_fwd: bad shape n2=%lld d=%lld ldz=%lld",
+                (long long)n2, (long long)d, (long long)ldz);
+  cudaStream_t st = (cudaStream_t)stream;
+  DAMSM_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  row_norm_kernel<<<(unsigned)((n2 + 7) / 8), 256, 0, st>>>(z, ldz, (int)n2, (int)d, nrm);
+  GemmDesc g{};
+  g.a = z; g.a_m = ldz; g.a_k = 1;
+  g.b = z; g.b_k = 1; g.b_n = ldz;
+  g.c = sim; g.c_m = n2; g.c_n = 1;
+  g.m = (int)n2; g.n = (int)n2; g.k = (int)d; g.batch = 1; g.alpha = 1.f; g.beta = 0.f;
+  int rc = launch_gemm_f32(g, st);
+  if (rc) return rc;
+  ntxent_row_kernel<<<(unsigned)n2, 256, 0, st>>>(sim, nrm, (int)n2, inv_temp, eps, row_lse, loss);
+  return check_launch("ntxent_fwd");
+}
+
+extern "C" int damsm_ntxent_bwd_f32(const float *z, int64_t ldz, int64_t n2, int64_t d, float inv_temp, float eps,
+                                    const float *sim, const float *nrm, const float *row_lse, const float *gout,
+                                    float *work, float *dz, void *stream) {
+  DAMSM_REQUIRE(z && sim && nrm && row_lse && gout && work && dz, "ntxent_bwd: null pointer");
+  DAMSM_REQUIRE(n2 >= 2 && n2 % 2 == 0 && d > 0 && ldz >= d, "ntxent_bwd: bad shape n2=%lld d=%lld ldz=%lld",
+                (long long)n2, (long long)d, (long long)ldz);
+  cudaStream_t st = (cudaStream_t)stream;
+  float *coef = work + n2 * n2;
+  DAMSM_CUDA(cudaMemsetAsync(coef, 0, sizeof(float) * n2, st));
+  ntxent_bwd_coef_kernel<<<(unsigned)n2, 256, 0, st>>>(sim, nrm, row_lse, gout, (int)n2, inv_temp, eps, work, coef);
+  GemmDesc g{};
+  // dz = W z + W^T z : z_x enters sim as row x and as column x
+  g.a = work; g.a_m = n2; g.a_k = 1;
+  g.b = z; g.b_k = ldz; g.b_n = 1;
+  g.c = dz; g.c_m = d; g.c_n = 1;
+  g.m = (int)n2; g.n = (int)d; g.k = (int)n2; g.batch = 1; g.alpha = 1.f; g.beta = 0.f;
+  int rc = launch_gemm_f32(g, st);
+  if (rc) return rc;
+  g.a_m = 1; g.a_k = n2; g.beta = 1.f;
+  rc = launch_gemm_f32(g, st);
+  if (rc) return rc;
+  norm_term_kernel<<<(unsigned)((n2 * d + 255) / 256), 256, 0, st>>>(dz, z, ldz, coef, nrm, (int)n2, (int)d);
+  return check_launch("ntxent_bwd");
 }

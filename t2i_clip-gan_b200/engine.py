@@ -223,6 +223,28 @@ class CudaEngine:
                   float(gamma3), float(eps), work.data_ptr(), da.data_ptr(), db.data_ptr(), _stream())
         return da, db
 
+    # ---- NT-Xent (nt_xent.py) -------------------------------------------------------------------------------
+    def ntxent_fwd(self, z, inv_temp, eps):
+        _require_cuda(z)
+        n2, d = z.shape
+        dev = z.device
+        sim = torch.empty((n2, n2), device=dev, dtype=torch.float32)
+        nrm = torch.empty(n2, device=dev, dtype=torch.float32)
+        row_lse = torch.empty(n2, device=dev, dtype=torch.float32)
+        loss = torch.empty(1, device=dev, dtype=torch.float32)
+        _lib.call("damsm_ntxent_fwd_f32", z.data_ptr(), z.stride(0), n2, d, float(inv_temp), float(eps),
+                  sim.data_ptr(), nrm.data_ptr(), row_lse.data_ptr(), loss.data_ptr(), _stream())
+        return loss, sim, nrm, row_lse
+
+    def ntxent_bwd(self, z, sim, nrm, row_lse, gout, inv_temp, eps):
+        n2, d = z.shape
+        work = torch.empty(n2 * n2 + n2, device=z.device, dtype=torch.float32)
+        dz = torch.empty((n2, d), device=z.device, dtype=torch.float32)
+        _lib.call("damsm_ntxent_bwd_f32", z.data_ptr(), z.stride(0), n2, d, float(inv_temp), float(eps),
+                  sim.data_ptr(), nrm.data_ptr(), row_lse.data_ptr(), gout.data_ptr(), work.data_ptr(),
+                  dz.data_ptr(), _stream())
+        return dz
+
     # ---- func_attention -----------------------------------------------------------------------------------------
     def func_attention_fwd(self, qhat, vhat, ctx3, mask_u8, gamma1):
         _require_cuda(qhat, vhat, ctx3, mask_u8)

@@ -290,6 +290,50 @@ def sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, eps=1e-8, *, ga
     return l0.to(out_dtype) if out_dtype != torch.float32 else l0, l1.to(out_dtype) if out_dtype != torch.float32 else l1
 
 
+# ----------------------------------------------------------------------------------------------- NT-Xent
+class DamsmNTXent(torch.autograd.Function):
+    """NT_Xent.forward (nt_xent.py:16-35) with the mask of masks.py:3-17: one GEMM + one row kernel instead of
+    the reference's (2B, 2B, D) broadcast."""
+
+    @staticmethod
+    def forward(ctx, z_i, z_j, inv_temp, eps, engine):
+        z = torch.cat((z_i, z_j), dim=0).contiguous()                # nt_xent.py:22
+        loss, sim, nrm, row_lse = engine.ntxent_fwd(z, inv_temp, eps)
+        ctx.engine, ctx.inv_temp, ctx.eps, ctx.b = engine, inv_temp, eps, z_i.shape[0]
+        ctx.save_for_backward(z, sim, nrm, row_lse)
+        return loss[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        z, sim, nrm, row_lse = ctx.saved_tensors
+        gout = g.reshape(1).to(torch.float32).contiguous()
+        dz = ctx.engine.ntxent_bwd(z, sim, nrm, row_lse, gout, ctx.inv_temp, ctx.eps)
+        b = ctx.b
+        return (dz[:b] if ctx.needs_input_grad[0] else None), (dz[b:] if ctx.needs_input_grad[1] else None), \
+            None, None, None
+
+
+def standard_ntxent_mask(batch_size):
+    """The mask both reference builders produce (masks.py:3-17): False on the diagonal and on the +-B diagonals."""
+    n2 = 2 * int(batch_size)
+    idx = torch.arange(n2)
+    same = idx.reshape(-1, 1) == idx.reshape(1, -1)
+    pair = (idx.reshape(-1, 1) - idx.reshape(1, -1)).abs() == int(batch_size)
+    return ~(same | pair)
+
+
+def nt_xent(z_i, z_j, temperature, *, eps=1e-8, engine=None):
+    """Functional form of ``NT_Xent(batch_size, temperature, mask, device)(z_i, z_j)`` (nt_xent.py:16-35)."""
+    if z_i.dim() != 2 or z_j.shape != z_i.shape:
+        raise ValueError("nt_xent: z_i and z_j must both be (B, D)")
+    if not (float(temperature) > 0.0):
+        raise ValueError("nt_xent: temperature must be positive")
+    eng = engine or get_engine("fp32")
+    out_dtype = z_i.dtype
+    loss = DamsmNTXent.apply(z_i.float(), z_j.float(), 1.0 / float(temperature), float(eps), eng)
+    return loss.to(out_dtype) if out_dtype != torch.float32 else loss
+
+
 # ----------------------------------------------------------------------------------------------- func_attention
 class DamsmFuncAttention(torch.autograd.Function):
     @staticmethod

@@ -216,3 +216,86 @@ def test_full_size_properties_c2():
     assert rel(dwp, dw[perm]) <= 1e-4
     radial = (dr * x["regions"]).sum(-1)                # d/ds of loss(s * v) at s=1 must vanish
     assert np.abs(radial).max() <= 1e-5 * np.abs(dr).max() * np.abs(x["regions"]).max() * 512 ** 0.5
+
+
+# ----------------------------------------------------------------------------------------------- NT-Xent
+@pytest.mark.parametrize("name", case_names())
+def test_nt_xent_vs_golden(name):
+    g = Golden(name)
+    x = g.x
+    zi = torch.tensor(x["sent"], device="cuda", requires_grad=True)
+    zj = torch.tensor(x["img"], device="cuda", requires_grad=True)
+    loss = pkg.nt_xent(zi, zj, g.scalar("ntx_temperature"))
+    loss.backward()
+    assert loss.dim() == 0
+    assert abs(loss.item() - g.scalar("ntx_loss")) <= TOL * max(1.0, abs(g.scalar("ntx_loss")))
+    assert g.rel_err("ntx_dzi", zi.grad.cpu().numpy()) <= TOL
+    assert g.rel_err("ntx_dzj", zj.grad.cpu().numpy()) <= TOL
+
+
+@pytest.mark.parametrize("B,D,temp", [(2, 8, 0.5), (3, 33, 0.07), (48, 512, 0.5), (300, 512, 0.5)])
+def test_nt_xent_vs_oracle_shapes(B, D, temp):
+    """Edge sizes: two pairs, odd D, the pretrain batch, a batch wider than one CTA pass."""
+    rng = np.random.default_rng(B * 1000 + D)
+    s = rng.standard_normal((B, D))
+    zi = (0.5 * s + rng.standard_normal((B, D))).astype(np.float32)
+    zj = (0.5 * s + rng.standard_normal((B, D))).astype(np.float32)
+    o = O.nt_xent(zi, zj, temp, g=0.2)                      # trainer.py:426 scales the term by 0.2
+    a = torch.tensor(zi, device="cuda", requires_grad=True)
+    b = torch.tensor(zj, device="cuda", requires_grad=True)
+    loss = pkg.nt_xent(a, b, temp)
+    (loss * 0.2).backward()
+    assert abs(loss.item() - o["loss"]) <= TOL * max(1.0, abs(o["loss"]))
+    assert rel(a.grad.cpu().numpy(), o["dz_i"]) <= TOL and rel(b.grad.cpu().numpy(), o["dz_j"]) <= TOL
+
+
+def test_nt_xent_single_pair_is_zero():
+    """B = 1: the only candidate of each row is its positive, so the loss and its gradient vanish."""
+    a = torch.randn(1, 16, device="cuda", requires_grad=True)
+    b = torch.randn(1, 16, device="cuda", requires_grad=True)
+    loss = pkg.nt_xent(a, b, 0.5)
+    loss.backward()
+    assert abs(loss.item()) <= 1e-6 and a.grad.abs().max().item() <= 1e-6 and b.grad.abs().max().item() <= 1e-6
+
+
+def test_nt_xent_module_drop_in():
+    """``from nt_xent import NT_Xent`` / ``from masks import mask_correlated_samples_2`` with the reference's call
+    shape (pretrain_DAMSM.py:445-449, :173); a strided view and a one-sided gradient."""
+    import os
+    import sys
+    pdir = os.path.dirname(os.path.abspath(pkg.__file__))
+    sys.path.insert(0, pdir)
+    try:
+        for m in ("nt_xent", "masks"):
+            sys.modules.pop(m, None)
+        from masks import mask_correlated_samples, mask_correlated_samples_2
+        from nt_xent import NT_Xent
+    finally:
+        sys.path.remove(pdir)
+    B, D = 12, 64
+    mask = mask_correlated_samples_2(B)
+    ref_mask = torch.ones((2 * B, 2 * B), dtype=torch.bool).fill_diagonal_(False)
+    for i in range(B):
+        ref_mask[i, B + i] = False
+        ref_mask[B + i, i] = False
+    assert torch.equal(mask, ref_mask)
+
+    class Args:
+        batch_size = B
+    assert torch.equal(mask_correlated_samples(Args()), ref_mask)
+    crit = NT_Xent(B, 0.5, mask, torch.device("cuda"))
+    rng = np.random.default_rng(5)
+    wide = torch.tensor(rng.standard_normal((B, 2 * D)).astype(np.float32), device="cuda")
+    zi = wide[:, :D].requires_grad_(True)                  # row stride 2*D
+    zj = torch.tensor(rng.standard_normal((B, D)).astype(np.float32), device="cuda")
+    loss = crit(zi, zj)
+    loss.backward()
+    o = O.nt_xent(wide[:, :D].detach().cpu().numpy(), zj.cpu().numpy(), 0.5)
+    assert abs(loss.item() - o["loss"]) <= TOL * max(1.0, abs(o["loss"]))
+    assert rel(zi.grad.cpu().numpy(), o["dz_i"]) <= TOL and zj.grad is None
+    bad = mask.clone()
+    bad[0, 1] = False
+    with pytest.raises(ValueError):
+        NT_Xent(B, 0.5, bad, torch.device("cuda"))
+    with pytest.raises(ValueError):
+        crit(zi[:5], zj[:5])

@@ -34,6 +34,16 @@ def test_sent_loss_oracle_matches_reference(name):
     assert g.rel_err("dtxt", o["dtxt"]) <= TOL_GRAD
 
 
+@pytest.mark.parametrize("name", case_names())
+def test_nt_xent_oracle_matches_reference(name):
+    g = Golden(name)
+    x = g.x
+    o = O.nt_xent(x["sent"], x["img"], g.scalar("ntx_temperature"))
+    assert abs(o["loss"] - g.scalar("ntx_loss")) <= TOL_LOSS * max(1.0, abs(g.scalar("ntx_loss")))
+    assert g.rel_err("ntx_dzi", o["dz_i"]) <= TOL_GRAD
+    assert g.rel_err("ntx_dzj", o["dz_j"]) <= TOL_GRAD
+
+
 @pytest.mark.parametrize("name", [n for n in case_names() if Golden(n).has("fa_wc")])
 def test_func_attention_oracle_matches_reference(name):
     g = Golden(name)
@@ -80,3 +90,12 @@ def test_attention_map_golden():
     blk = O._pair_block(q[0], u[0], (x["mask"][0] != 0).astype(float), v, G, g.gammas[0], g.gammas[1])
     # reference attn_maps[0] is (B, R, T): softmax over words of caption 0 vs every image
     assert g.rel_err("attn0", blk["P"].transpose(0, 2, 1)) <= TOL_GRAD
+
+
+@pytest.mark.parametrize("name", ["tiny_b6_t5_r9_cls", "c2_coco_b48_t18_r49"])
+def test_ntxent_procedure_port_matches_reference(name):
+    """oracle/ref_port.ntxent_step (bench.py's CPU baseline for the NT-Xent workloads)."""
+    g = Golden(name)
+    r = ref_port.ntxent_step(g.x["sent"], g.x["img"], g.scalar("ntx_temperature"))
+    assert abs(r["loss"] - g.scalar("ntx_loss")) <= 1e-5 * max(1.0, abs(g.scalar("ntx_loss")))
+    assert g.rel_err("ntx_dzi", r["dz_i"]) <= 2e-5 and g.rel_err("ntx_dzj", r["dz_j"]) <= 2e-5

@@ -36,3 +36,15 @@ def test_general_mask_not_prefix():
     ref = RS.ref_words_loss(x["words"], x["regions"], m, x["labels"], None, (4, 5, 10))
     o = O.words_loss(x["words"], x["regions"], m, x["labels"], None, 4.0, 5.0, 10.0)
     assert abs(o["loss0"] - ref["loss0"]) < 2e-6 and rel(o["dwords"], ref["dwords"]) < 5e-6
+
+
+@pytest.mark.parametrize("B,temp,seed", [(2, 0.5, 1), (7, 0.5, 2), (24, 0.1, 3)])
+def test_live_nt_xent(B, temp, seed):
+    rng = np.random.default_rng(seed)
+    s = rng.standard_normal((B, 1, 64))
+    zi = (0.5 * s[:, 0] + rng.standard_normal((B, 64))).astype(np.float32)
+    zj = (0.5 * s[:, 0] + rng.standard_normal((B, 64))).astype(np.float32)
+    ref = RS.ref_nt_xent(zi, zj, temp)
+    o = O.nt_xent(zi, zj, temp)
+    assert abs(o["loss"] - ref["loss"]) < 2e-6 * max(1, abs(ref["loss"]))
+    assert rel(o["dz_i"], ref["dz_i"]) < 5e-6 and rel(o["dz_j"], ref["dz_j"]) < 5e-6
