@@ -676,7 +676,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               if (valid && !DBG(p, 1)) {
                 // streaming stores: the scratch is written once and read back by the GEMMs much later
                 __stcs(o_ds + c, make_uint4(pk_ds[0], pk_ds[1], pk_ds[2], pk_ds[3]));
-                __stcs(o_a + c, make_uint4(pk_a[0], pk_a[1], pk_a[2], pk_a[3]));
+                if (p.x_a) __stcs(o_a + c, make_uint4(pk_a[0], pk_a[1], pk_a[2], pk_a[3]));
               }
             }
           }
@@ -901,7 +901,8 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
                                   float gamma2, float gamma3, void *workspace, int64_t workspace_bytes, float *dqhat,
                                   float *dvhat, float *hmat, float *kq, void *stream) {
   DAMSM_REQUIRE(qhat16 && vhat16 && gx && unorm && mask && sim && stats && row_lse && col_lse && gscale && workspace &&
-                    dqhat && dvhat && hmat && kq, "words_bwd_tc: null pointer");
+                    kq, "words_bwd_tc: null pointer");
+  DAMSM_REQUIRE((dvhat == nullptr) == (hmat == nullptr), "words_bwd_tc: dvhat and hmat must be given together");
   const int64_t tp = (t + 7) / 8 * 8;
   DAMSM_REQUIRE(q_rows == tp, "words_bwd_tc: qhat16 must be padded to %lld rows per caption (got %lld)", (long long)tp,
                 (long long)q_rows);
@@ -938,7 +939,7 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
     p.stats = const_cast<float *>(stats);
     p.i0 = (int)i0; p.tp = (int)tp; p.kc = kc; p.row_lse = row_lse; p.col_lse = col_lse; p.gscale = gscale;
     p.labels = labels; p.row_offset = row_offset; p.b_total = b_total; p.kq = kq;
-    p.x_ds = x_ds; p.x_a = x_a; p.svec = svec; p.scale_ds = scale_ds; p.scale_ba = scale_ba;
+    p.x_ds = x_ds; p.x_a = hmat ? x_a : nullptr; p.svec = svec; p.scale_ds = scale_ds; p.scale_ba = scale_ba;
     p.dbg = getenv("DAMSM_DBG") ? atoi(getenv("DAMSM_DBG")) : 0;
     if ((rc = tc_launch<true>(tl, p, bi, st))) return rc;
     if (getenv("DAMSM_BWD_FUSED_ONLY")) continue;   // bench.py times the fused recompute kernel alone this way
@@ -949,15 +950,17 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
     }
     const __half *qc = (const __half *)qhat16 + i0 * tp * d;
     // dvhat (bc*R x D) += X_dS (bc*R x kc) . qhat_chunk (kc x D)            [row-major view; cuBLAS is column-major]
-    DAMSM_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)d, (int)n_rows, (int)kc, &inv_ds, qc, CUDA_R_16F, (int)d,
-                              x_ds, CUDA_R_16F, (int)kc, &one, dvhat, CUDA_R_32F, (int)d, CUBLAS_COMPUTE_32F,
-                              CUBLAS_GEMM_DEFAULT_TENSOR_OP));
+    if (dvhat)
+      DAMSM_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)d, (int)n_rows, (int)kc, &inv_ds, qc, CUDA_R_16F,
+                                (int)d, x_ds, CUDA_R_16F, (int)kc, &one, dvhat, CUDA_R_32F, (int)d, CUBLAS_COMPUTE_32F,
+                                CUBLAS_GEMM_DEFAULT_TENSOR_OP));
     // dqhat_chunk (kc x D) = X_dS^T (kc x bc*R) . vhat (bc*R x D)
-    DAMSM_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, (int)d, (int)kc, (int)n_rows, &inv_ds, vhat16, CUDA_R_16F,
-                              (int)d, x_ds, CUDA_R_16F, (int)kc, &zero, dqhat + i0 * tp * d, CUDA_R_32F, (int)d,
-                              CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT_TENSOR_OP));
+    if (dqhat)
+      DAMSM_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, (int)d, (int)kc, (int)n_rows, &inv_ds, vhat16, CUDA_R_16F,
+                                (int)d, x_ds, CUDA_R_16F, (int)kc, &zero, dqhat + i0 * tp * d, CUDA_R_32F, (int)d,
+                                CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT_TENSOR_OP));
     // H_j (R x R) += sum_k s_k A_j[:,k] A_j[:,k]^T: own tcgen05 kernel (hmat_tc.cu), one CTA per image
-    if ((rc = launch_hmat_tc(x_a, svec, bc, r, kc, inv_ba, hmat, st))) return rc;
+    if (hmat && (rc = launch_hmat_tc(x_a, svec, bc, r, kc, inv_ba, hmat, st))) return rc;
   }
   return 0;
 }

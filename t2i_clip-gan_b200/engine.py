@@ -125,17 +125,18 @@ class CudaEngine:
         return sim
 
     def words_bwd(self, qhat, qhat16, vhat, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
-                  row_offset, b_total, gammas):
+                  row_offset, b_total, gammas, need_dq=True, need_dv=True):
         """Returns (dqhat (br,T,D), dvhat (bc,R,D), hmat (bc,R,R), kq (br,T)); dvhat and hmat are partial sums over
         this rank's caption rows and dvhat does not yet contain the -H vhat term (see gram_bwd).  ``vhat`` is only
-        read by the fp32 path."""
+        read by the fp32 path.  Tensor-core path: ``need_dq`` / ``need_dv`` = False skip that side's GEMMs and return
+        None for it (the fp32 path always computes both)."""
         gram = col["gram"]
         br, t, d = qhat.shape
         bc, r, _ = gram.shape
         dev = qhat.device
         if self.precision == "bf16":
             return self._words_bwd_tc(qhat16, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
-                                      row_offset, b_total, gammas, br, bc, t, r, d)
+                                      row_offset, b_total, gammas, br, bc, t, r, d, need_dq, need_dv)
         dqhat = torch.zeros((br, t, d), device=dev, dtype=torch.float32)
         dvhat = torch.zeros((bc, r, d), device=dev, dtype=torch.float32)
         hmat = torch.zeros((bc, r, r), device=dev, dtype=torch.float32)
@@ -152,7 +153,7 @@ class CudaEngine:
     tc_workspace_bytes = None
 
     def _words_bwd_tc(self, qhat16, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
-                      row_offset, b_total, gammas, br, bc, t, r, d):
+                      row_offset, b_total, gammas, br, bc, t, r, d, need_dq=True, need_dv=True):
         dev = qhat16.device
         tp = qhat16.shape[1]
         lib = _lib.load()
@@ -162,19 +163,20 @@ class CudaEngine:
             budget = max(6 << 30, torch.cuda.mem_get_info(dev)[0] // 3)
         ws_bytes = min(max(row_bytes, budget // row_bytes * row_bytes), row_bytes * br)
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-        dqhat = torch.empty((br, tp, d), device=dev, dtype=torch.float32)
-        dvhat = torch.zeros((bc, r, d), device=dev, dtype=torch.float32)
-        hmat = torch.zeros((bc, r, r), device=dev, dtype=torch.float32)
+        dqhat = torch.empty((br, tp, d), device=dev, dtype=torch.float32) if need_dq else None
+        dvhat = torch.zeros((bc, r, d), device=dev, dtype=torch.float32) if need_dv else None
+        hmat = torch.zeros((bc, r, r), device=dev, dtype=torch.float32) if need_dv else None
         kq = torch.zeros((br, t), device=dev, dtype=torch.float32)
         _lib.call("damsm_words_bwd_tc", qhat16.data_ptr(), tp, col["vhat16"].data_ptr(), col["gx"].data_ptr(),
                   unorm.data_ptr(), mask_u8.data_ptr(), sim.data_ptr(), col["stats"].data_ptr(),
                   row_lse.data_ptr(), col_lse.data_ptr(),
                   _lib.ptr(labels), gscale.data_ptr(), int(row_offset), int(b_total), br, bc, t, r, d,
                   float(gammas[0]), float(gammas[1]), float(gammas[2]), ws.data_ptr(), ws_bytes,
-                  dqhat.data_ptr(), dvhat.data_ptr(), hmat.data_ptr(), kq.data_ptr(), _stream())
+                  _lib.ptr(dqhat), _lib.ptr(dvhat), _lib.ptr(hmat), kq.data_ptr(), _stream())
         chunks = -(-br // max(1, ws_bytes // row_bytes))
-        _lib.add_launches(2 * chunks - 1)          # own kernels per chunk: fused recompute + hmat (cuBLAS not counted)
-        return dqhat[:, :t, :], dvhat, hmat, kq
+        # own kernels per chunk: fused recompute + hmat (cuBLAS not counted)
+        _lib.add_launches((2 if need_dv else 1) * chunks - 1)
+        return (dqhat[:, :t, :] if need_dq else None), dvhat, hmat, kq
 
     # ---- masked bidirectional cross-entropy ---------------------------------------------------------------
     def ce_stats(self, logits, cls_rows, cls_cols, row_offset):

@@ -108,7 +108,8 @@ class DamsmWordsLoss(torch.autograd.Function):
         eng, colside = ctx.engine, ctx.colside
         gscale = torch.stack([g0.reshape(()), g1.reshape(())]).to(torch.float32)
         dqhat, dvhat, hmat, kq = eng.words_bwd(qhat, ctx.qhat16, vhat, colside, qunorm, mask_u8, sim, row_lse, col_lse,
-                                               labels, gscale, ctx.row_offset, ctx.b_total, ctx.gammas)
+                                               labels, gscale, ctx.row_offset, ctx.b_total, ctx.gammas,
+                                               need_dq=ctx.needs_input_grad[1], need_dv=ctx.needs_input_grad[0])
         dregions3 = dwords3 = None
         if ctx.needs_input_grad[0]:
             # partial sums over this rank's captions for ALL images -> owners; the -H vhat term is applied there

@@ -90,3 +90,23 @@ def test_tc_multi_chunk_backward_matches_exact_path():
     assert abs(a[0] - b[0]) <= TOL * max(1, abs(b[0])) and abs(a[1] - b[1]) <= TOL * max(1, abs(b[1]))
     assert rel(a[2], b[2]) <= TOL
     assert rel(a[3], b[3]) <= TOL
+
+
+@pytest.mark.parametrize("side", ["regions", "words"])
+def test_tc_one_sided_gradients(side):
+    """Only one input requires grad (image side only = the DM-GAN generator step, trainer.py:338 / SURVEY 8f-4): the
+    other side's GEMMs are skipped and the remaining gradient is unchanged."""
+    B, T, R = 6, 77, 49
+    x = rounded(O.make_inputs(B, T, R, seed=31, class_ids=True, n_classes=3))
+    o = O.words_loss(x["words"], x["regions"], x["mask"], x["labels"], x["class_ids"], 4.0, 5.0, 10.0)
+    w = torch.tensor(x["words"], device="cuda").requires_grad_(side == "words")
+    r = torch.tensor(x["regions"], device="cuda").requires_grad_(side == "regions")
+    before = pkg._lib.launch_count()
+    l0, l1, _ = pkg.words_loss(r.permute(0, 2, 1), w.permute(0, 2, 1), torch.arange(B, device="cuda"), None,
+                               x["class_ids"], B, torch.tensor(x["mask"]), 4.0, 5.0, 10.0, precision="bf16")
+    (l0 + l1).backward()
+    assert pkg._lib.launch_count() > before
+    if side == "regions":
+        assert w.grad is None and rel(r.grad.cpu().numpy(), o["dregions"]) <= TOL
+    else:
+        assert r.grad is None and rel(w.grad.cpu().numpy(), o["dwords"]) <= TOL
