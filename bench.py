@@ -40,6 +40,9 @@ WORKLOADS = {
     # the NT-Xent term of the same training loss (nt_xent.py), its own metric
     "ntx48": dict(B=48, ntxent=True, temperature=0.5, seed=2031, desc="NT-Xent, pretrain batch (pretrain_DAMSM.py:445-449)"),
     "ntx4096": dict(B=4096, ntxent=True, temperature=0.5, seed=2032, desc="NT-Xent at the scaling-sweep batch"),
+    # rm_special_token (pretrain_DAMSM.py:58-79), the step right before words_loss
+    "rmtok48": dict(B=48, n=30, rmtok=True, seed=2033, desc="rm_special_token, pretrain batch, words_num=30"),
+    "rmtok4096": dict(B=4096, n=79, rmtok=True, seed=2034, desc="rm_special_token at the scaling-sweep batch, 77+2 tokens"),
 }
 
 
@@ -286,6 +289,113 @@ def run_ntxent(args, w):
                           gpu_launches=launches, roofline=roof, cpu_baseline=base)))
 
 
+# --------------------------------------------------------------------------------------------- rm_special_token (8f-3)
+def rmtok_inputs(w):
+    g = torch.Generator().manual_seed(w["seed"])
+    B, n = w["B"], w["n"]
+    lens = torch.randint(2, n + 1, (B,), generator=g)
+    mask = (torch.arange(n).reshape(1, n) < lens.reshape(B, 1)).to(torch.int64)
+    return mask, torch.randn(B, n, D, generator=g)
+
+
+def rmtok_cpu(w, steps, budget_s=20.0):
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = w["B"]
+    Bs = min(B, 256)
+    mask, emb = rmtok_inputs(dict(w, B=Bs))
+    dout = torch.randn(Bs, w["n"] - 2, D).numpy()
+    ref_port.rm_special_token_step(mask.numpy(), emb.numpy(), dout)
+    ts = []
+    t_end = time.perf_counter() + budget_s
+    while len(ts) < steps and (time.perf_counter() < t_end or len(ts) < 2):
+        t0 = time.perf_counter()
+        ref_port.rm_special_token_step(mask.numpy(), emb.numpy(), dout)
+        ts.append(time.perf_counter() - t0)
+    t_sample = float(np.median(ts))
+    t_full = t_sample * (B / Bs)
+    return dict(value=B / t_full, unit="captions/s", cores=cores, kind="port",
+                sample=(f"B={Bs} captions of {w['n']} tokens, D={D}, fp32, fwd+bwd, median of {len(ts)}; "
+                        + ("full size" if Bs == B else f"extrapolated to B={B} with time ~ B")),
+                measured_ms_per_sample_step=t_sample * 1e3, sample_batch=Bs), t_full
+
+
+def run_rmtok(args, w):
+    """One step = rm_special_token forward + backward of a random upstream gradient; value = captions/s."""
+    B, n = w["B"], w["n"]
+    cfgd = dict(workload=args.workload, description=w["desc"], B=B, tokens=n, D=D)
+    if args.impl == "reference":
+        base, t_full = rmtok_cpu(w, args.steps)
+        print(json.dumps(dict(metric="rm_special_token_fwd_bwd_captions_per_s", value=base["value"], unit="captions/s",
+                              impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                              ms_per_step=t_full * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                              dtype="f32", data="synthetic", config=cfgd, cpu_baseline=base,
+                              e2e=dict(value=base["value"], unit="captions/s", h2d_bytes_per_step=0,
+                                       d2h_bytes_per_step=0))))
+        return
+    pkg = importlib.import_module("t2i_clip-gan_b200")
+    torch.cuda.set_device(0)
+    mask_h, emb_h = rmtok_inputs(w)
+    mask_h, emb_h = mask_h.pin_memory(), emb_h.pin_memory()
+    mask, emb = mask_h.cuda(), emb_h.cuda().requires_grad_(True)
+    dout = torch.randn(B, n - 2, D, device="cuda")
+
+    def step(m, x):
+        out, m_new = pkg.rm_special_token(m, x)
+        out.backward(dout)
+        return m_new
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for _ in range(args.warmup):
+        emb.grad = None
+        step(mask, emb)
+    torch.cuda.synchronize()
+    pkg._lib.reset_launch_count()
+    sampler = ClockSampler(0)
+    evs = []
+    for _ in range(args.steps):
+        emb.grad = None
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(mask, emb)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    launches = pkg._lib.launch_count()
+    clocks = sampler.stop()
+    ms_step = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    out_pinned = torch.empty(B, n - 2, dtype=torch.int64).pin_memory()
+    t0 = None
+    for it in range(args.steps + 2):
+        if it == 2:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        x = emb_h.to("cuda", non_blocking=True).requires_grad_(True)
+        m = mask_h.to("cuda", non_blocking=True)
+        out_pinned.copy_(step(m, x), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    peaks = load_peaks()
+    # algorithmic HBM bytes: fwd reads and writes the kept rows, bwd reads them and writes all n rows (+ the masks)
+    alg_bytes = 4.0 * B * D * (3 * (n - 2) + n) + 8.0 * B * (3 * n - 2)
+    gbs = alg_bytes / (ms_step * 1e-3) / 1e9
+    roof = dict(bound="hbm", achieved=gbs, peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"], traffic=None,
+                peak_source=peaks["src"], note="two launches (gather, scatter); latency-bound at the pretrain batch")
+    base = None if args.no_cpu_baseline else rmtok_cpu(w, 5)[0]
+    print(json.dumps(dict(metric="rm_special_token_fwd_bwd_captions_per_s", value=B / (ms_step * 1e-3), unit="captions/s",
+                          n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True,
+                          scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                          config=dict(cfgd, l2="L2 flushed (256 MiB memset) between timed iterations",
+                                      step="rm_special_token forward + backward"),
+                          clocks=clocks,
+                          e2e=dict(value=B / e2e_s, unit="captions/s", ms_per_step=e2e_s * 1e3,
+                                   h2d_bytes_per_step=int(emb_h.numel() * 4 + mask_h.numel() * 8),
+                                   d2h_bytes_per_step=int(out_pinned.numel() * 8)),
+                          gpu_launches=launches, roofline=roof, cpu_baseline=base)))
+
+
 # --------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -308,9 +418,9 @@ def main():
     if args.steps is None:
         args.steps = 5 if w["B"] >= 1024 else 20
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if w.get("ntxent"):
-        if int(os.environ.get("RANK", "0")) == 0:      # replicas only: the term is O(B^2 D), not sharded
-            run_ntxent(args, w)
+    if w.get("ntxent") or w.get("rmtok"):
+        if int(os.environ.get("RANK", "0")) == 0:      # replicas only: small side operators, not sharded
+            (run_ntxent if w.get("ntxent") else run_rmtok)(args, w)
         return
 
     if args.impl == "reference":

@@ -167,6 +167,18 @@ DAMSM_API int damsm_ntxent_bwd_f32(const float *z, int64_t ldz, int64_t n2, int6
                          const float *sim, const float *nrm, const float *row_lse, const float *gout,
                          float *work, float *dz, void *stream);
 
+/* ---- rm_special_token (pretrain_DAMSM.py:58-79; called at :128-129 right before words_loss) ----------------
+ * x (b,n,d) elements of elem_bytes (2 or 4), batch / token strides sb, sn in ELEMENTS, innermost dim contiguous;
+ * mask (b,n) int64 with element strides msb, msn.  L_i = index of the first 0 of mask row i (n if none, clamped
+ * to >= 2).  out (b,n-2,d) contiguous: out[i][k] = x[i][k+1] for k < L_i-2, x[i][k+2] otherwise;
+ * out_mask (b,n-2) int64 contiguous (may be NULL) is gathered the same way.  Needs n >= 3. */
+DAMSM_API int damsm_rm_special_token_fwd(const void *x, int64_t elem_bytes, int64_t b, int64_t n, int64_t d,
+                               int64_t sb, int64_t sn, const int64_t *mask, int64_t msb, int64_t msn,
+                               void *out, int64_t *out_mask, void *stream);
+/* dout (b,n-2,d) contiguous -> dx (b,n,d) contiguous, OVERWRITTEN (zero rows at the removed tokens) */
+DAMSM_API int damsm_rm_special_token_bwd(const void *dout, int64_t elem_bytes, int64_t b, int64_t n, int64_t d,
+                               const int64_t *mask, int64_t msb, int64_t msn, void *dx, void *stream);
+
 /* ---- func_attention (GlobalAttention.py:38-160): one (caption b, image b) pair per batch element -------
  * wc (B,T,D) = A . context_RAW (line :153), attn (B,T,R) = softmax over words (line :104),
  * attn2 (B,T,R) = softmax over regions of gamma1*attn (saved for backward).

@@ -273,6 +273,25 @@ def nt_xent(z_i, z_j, temperature, g=1.0):
     return dict(loss=loss, sim=sim, dz_i=dz[:b], dz_j=dz[b:])
 
 
+# --------------------------------------------------------------------------- rm_special_token
+def rm_special_token(mask, words_emb):
+    """pretrain_DAMSM.py:58-79.  Per caption: no 0 in the mask -> rows 1..n-2 (:67-69); else with e = index of the
+    first 0 -> rows 1..e-2 followed by rows e..n-1 (:71-75), i.e. <sos> (row 0) and <eos> (row e-1) are removed.
+    Returns (words_emb_new (B, n-2, D), mask_new (B, n-2), src (B, n-2) source row of every output row)."""
+    mask = np.asarray(mask)
+    words_emb = np.asarray(words_emb)
+    b, n = mask.shape
+    src = np.empty((b, n - 2), np.int64)
+    for i in range(b):
+        zeros = np.nonzero(mask[i] == 0)[0]
+        e = int(zeros.min()) if zeros.size else n
+        keep = [k for k in range(n) if k != 0 and k != e - 1]
+        assert len(keep) == n - 2, "caption with fewer than two leading 1s: undefined in the reference"
+        src[i] = keep
+    rows = np.arange(b)[:, None]
+    return words_emb[rows, src], mask[rows, src], src
+
+
 # --------------------------------------------------------------------------- func_attention
 def func_attention(query, context, gamma1, query_mask, d_wc=None):
     """GlobalAttention.py:38-160.

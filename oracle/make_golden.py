@@ -64,9 +64,39 @@ def digest(x):
     return h.hexdigest()
 
 
+def rm_special_inputs(seed, B, n, D):
+    """Seeded (mask, words_emb) the way the tokenizer pads them: <sos> w.. <eos> pad.. (prefix masks), including a
+    full row (no padding) and the shortest caption (<sos><eos> only)."""
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(2, n + 1, B)
+    lens[0], lens[1 % B] = n, 2
+    mask = (np.arange(n)[None, :] < lens[:, None]).astype(np.int64)
+    return mask, rng.standard_normal((B, n, D)).astype(np.float32)
+
+
+RM_CASES = {"rm_b7_n30_d16": (5, 7, 30, 16), "rm_b48_n30_d512": (6, 48, 30, 512), "rm_b5_n79_d512": (7, 5, 79, 512)}
+
+
+def main_rm(out_dir):
+    """rm_special_token (pretrain_DAMSM.py:58-79) outputs of the reference's own function -> tests/golden/aux/."""
+    aux = os.path.join(out_dir, "aux")
+    os.makedirs(aux, exist_ok=True)
+    for name, (seed, B, n, D) in RM_CASES.items():
+        mask, emb = rm_special_inputs(seed, B, n, D)
+        e, m = RS.ref_rm_special_token(mask, emb)
+        rec = dict(meta=np.array([seed, B, n, D], np.int64), mask_new=m.astype(np.int64),
+                   emb_sum=np.float64(e.astype(np.float64).sum()), emb_l2=np.float64(np.sqrt((e.astype(np.float64) ** 2).sum())),
+                   emb_sample=e.reshape(-1)[::SAMPLE_STRIDE].copy())
+        np.savez_compressed(os.path.join(aux, name + ".npz"), **rec)
+        print(f"{name}: out {e.shape}, kept-mask sum {int(m.sum())}")
+
+
 def main():
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "rm_special_token":      # only the token-gather fixtures
+        return main_rm(out_dir)
+    main_rm(out_dir)
     for name, (B, T, R, seed, cls, ncls) in CASES.items():
         x = O.make_inputs(B, T, R, seed=seed, class_ids=cls, n_classes=max(ncls, 1))
         w = RS.ref_words_loss(x["words"], x["regions"], x["mask"], x["labels"], x["class_ids"], GAMMAS)

@@ -129,3 +129,24 @@ def ntxent_step(z_i, z_j, temperature):
     loss = torch.nn.functional.cross_entropy(logits, torch.zeros(n2, dtype=torch.long), reduction="sum") / n2
     loss.backward()
     return dict(loss=float(loss.detach()), dz_i=a.grad.numpy().copy(), dz_j=b.grad.numpy().copy())
+
+
+def rm_special_token_step(mask, words_emb, dout):
+    """rm_special_token forward + backward the way the reference runs it (pretrain_DAMSM.py:58-79): a Python loop over
+    the batch, one boolean reduction / torch.where per caption, slices + cat, a final stack.  Returns (out, mask_new, dx)."""
+    x = torch.tensor(np.asarray(words_emb), requires_grad=True)
+    m = torch.tensor(np.asarray(mask))
+    n = x.shape[1]
+    embs, masks = [], []
+    for i in range(x.shape[0]):
+        if int(m[i].sum()) == n:                                    # no padding: <eos> is the last row
+            sel = slice(1, n - 1)
+            embs.append(x[i, sel, :])
+            masks.append(m[i, sel])
+        else:
+            e = int(torch.where(m[i] == 0)[0].min())                # first padding position; <eos> sits at e - 1
+            embs.append(torch.cat([x[i, 1:e - 1, :], x[i, e:, :]], dim=0))
+            masks.append(torch.cat([m[i, 1:e - 1], m[i, e:]], dim=0))
+    out = torch.stack(embs, dim=0)
+    out.backward(torch.tensor(np.asarray(dout)))
+    return out.detach().numpy(), torch.stack(masks, dim=0).numpy(), x.grad.numpy()

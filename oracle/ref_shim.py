@@ -167,3 +167,19 @@ def ref_nt_xent(z_i, z_j, temperature):
     loss = crit(a, b)
     loss.backward()
     return dict(loss=float(loss.detach()), dz_i=a.grad.numpy().copy(), dz_j=b.grad.numpy().copy())
+
+
+def ref_rm_special_token(mask, words_emb):
+    """Run the reference's own ``rm_special_token`` (pretrain_DAMSM.py:58-79).  The script cannot be imported (its
+    top level needs tensorboardX, nltk, ...), so the function's source is cut out of the file with ``ast`` at run time
+    and executed in a namespace that only holds torch -- nothing is copied into this repository."""
+    import ast
+    import numpy as np
+    import torch
+    path = os.path.join(REF_ROOT, "pretrain_DAMSM.py")
+    src = open(path).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "rm_special_token")
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    emb, m = ns["rm_special_token"](torch.as_tensor(np.asarray(mask)), torch.as_tensor(np.asarray(words_emb)))
+    return emb.numpy().copy(), m.numpy().copy()

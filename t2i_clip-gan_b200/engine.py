@@ -247,6 +247,25 @@ class CudaEngine:
                   dz.data_ptr(), _stream())
         return dz
 
+    # ---- rm_special_token (pretrain_DAMSM.py:58-79) ------------------------------------------------------------
+    def rm_special_token_fwd(self, x, mask_i64):
+        """x (B,n,D) with a contiguous innermost dim, 2- or 4-byte elements; mask_i64 (B,n) int64."""
+        _require_cuda(x, mask_i64)
+        b, n, d = x.shape
+        out = torch.empty((b, n - 2, d), device=x.device, dtype=x.dtype)
+        out_mask = torch.empty((b, n - 2), device=x.device, dtype=torch.int64)
+        _lib.call("damsm_rm_special_token_fwd", x.data_ptr(), x.element_size(), b, n, d, x.stride(0), x.stride(1),
+                  mask_i64.data_ptr(), mask_i64.stride(0), mask_i64.stride(1), out.data_ptr(), out_mask.data_ptr(),
+                  _stream())
+        return out, out_mask
+
+    def rm_special_token_bwd(self, dout, mask_i64, n):
+        b, _, d = dout.shape
+        dx = torch.empty((b, n, d), device=dout.device, dtype=dout.dtype)
+        _lib.call("damsm_rm_special_token_bwd", dout.data_ptr(), dout.element_size(), b, n, d, mask_i64.data_ptr(),
+                  mask_i64.stride(0), mask_i64.stride(1), dx.data_ptr(), _stream())
+        return dx
+
     # ---- func_attention -----------------------------------------------------------------------------------------
     def func_attention_fwd(self, qhat, vhat, ctx3, mask_u8, gamma1):
         _require_cuda(qhat, vhat, ctx3, mask_u8)

@@ -335,6 +335,41 @@ def nt_xent(z_i, z_j, temperature, *, eps=1e-8, engine=None):
     return loss.to(out_dtype) if out_dtype != torch.float32 else loss
 
 
+# ----------------------------------------------------------------------------------------------- rm_special_token
+class DamsmRmSpecialToken(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, words_emb, mask_i64, engine):
+        out, out_mask = engine.rm_special_token_fwd(words_emb, mask_i64)
+        ctx.engine, ctx.n = engine, words_emb.shape[1]
+        ctx.save_for_backward(mask_i64)
+        ctx.mark_non_differentiable(out_mask)
+        return out, out_mask
+
+    @staticmethod
+    def backward(ctx, dout, _dmask):
+        (mask_i64,) = ctx.saved_tensors
+        return ctx.engine.rm_special_token_bwd(dout.contiguous(), mask_i64, ctx.n), None, None
+
+
+def rm_special_token(mask, words_emb, *, engine=None):
+    """Drop-in for ``rm_special_token`` (pretrain_DAMSM.py:58-79): removes the <sos> row and the <eos> row (the one
+    before the first 0 of the attention mask; the last row when the mask has no 0) from ``words_emb`` (B, n, D) and
+    ``mask`` (B, n); returns ``(words_emb_new (B, n-2, D), mask_new (B, n-2))``.  One gather kernel, no host sync.
+    A caption whose mask starts with fewer than two 1s makes the reference's ``torch.stack`` fail; here it is treated
+    as <sos><eos> only."""
+    if words_emb.dim() != 3 or mask.dim() != 2 or mask.shape != words_emb.shape[:2]:
+        raise ValueError("rm_special_token: words_emb must be (B, n, D) and mask (B, n)")
+    if words_emb.shape[1] < 3:
+        raise ValueError("rm_special_token: need at least 3 tokens per caption")
+    if words_emb.element_size() not in (2, 4):
+        raise TypeError(f"rm_special_token: unsupported dtype {words_emb.dtype}")
+    eng = engine or get_engine("fp32")
+    x = words_emb if words_emb.stride(2) == 1 else words_emb.contiguous()
+    m64 = mask.to(device=words_emb.device, dtype=torch.int64)
+    out, out_mask = DamsmRmSpecialToken.apply(x, m64, eng)
+    return out, (out_mask if mask.dtype == torch.int64 else out_mask.to(mask.dtype))
+
+
 # ----------------------------------------------------------------------------------------------- func_attention
 class DamsmFuncAttention(torch.autograd.Function):
     @staticmethod
