@@ -92,7 +92,7 @@ class CheckerEngine:
         return g
 
     def words_bwd(self, qhat, qhat16, vhat, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
-                  row_offset, b_total, gammas):
+                  row_offset, b_total, gammas, need_dq=True, need_dv=True):
         g = self._g(sim, row_lse, col_lse, labels, gscale, row_offset, b_total)
         q, v, u = _np(qhat), _np(vhat), _np(unorm)
         blocks = self._blocks(qhat, vhat, col, unorm, mask_u8, gammas)
