@@ -600,7 +600,9 @@ def measure_roofline(pkg, w, dev, bl, B, rank, group, prec):
     # DRAM traffic of the two fused tcgen05 kernels per scored pair, from the committed ncu --set full capture
     # (profiles/r1_ncu_tc_summary.md: forward 2.8 KB, backward 71.6 KB -- the fp16 dS/A scratch rows); fp32 path: none captured
     traffic = (2.8e3 + 71.6e3) * bl * B if prec == "bf16" else None
+    sustained = peaks.get("bf16_sustained")
     return dict(bound="tensor", achieved=ach, peak=peaks["bf16"], unit="TFLOP/s", frac=ach / peaks["bf16"],
+                peak_sustained=sustained, frac_of_sustained=(ach / sustained if sustained else None),
                 traffic=traffic, traffic_note="bytes per step of the fused fwd+bwd kernels = ncu dram bytes per pair x pairs", peak_source=peaks["src"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
                 kernel=("word-loss operator: words_tc_kernel<FWD> (1 launch) + backward (words_tc_kernel<BWD> per chunk, "
                         "hmat_tc_kernel, 2 cuBLAS GEMMs per chunk); algorithmic flops (4+8)*B_rows*B*T*R*D"
