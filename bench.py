@@ -42,6 +42,10 @@ WORKLOADS = {
     "ntx4096": dict(B=4096, ntxent=True, temperature=0.5, seed=2032, desc="NT-Xent at the scaling-sweep batch"),
     # rm_special_token (pretrain_DAMSM.py:58-79), the step right before words_loss
     "rmtok48": dict(B=48, n=30, rmtok=True, seed=2033, desc="rm_special_token, pretrain batch, words_num=30"),
+    # linear_subr 768->512 + CLS drop fused with the l2norm prologue (model.py:46,78)
+    "proj48": dict(B=48, R=49, K=768, N=512, proj=True, in_dtype="fp32", seed=2035, desc="region projection, pretrain batch, ViT-B/32"),
+    "proj4096": dict(B=4096, R=196, K=768, N=512, proj=True, in_dtype="bf16", seed=2036,
+                     desc="region projection at the scaling-sweep batch, ViT-B/16, bf16 in"),
     "rmtok4096": dict(B=4096, n=79, rmtok=True, seed=2034, desc="rm_special_token at the scaling-sweep batch, 77+2 tokens"),
 }
 
@@ -396,6 +400,136 @@ def run_rmtok(args, w):
                           gpu_launches=launches, roofline=roof, cpu_baseline=base)))
 
 
+# --------------------------------------------------------------------------------------------- region projection (8f-2)
+def proj_inputs(w, B=None):
+    g = torch.Generator().manual_seed(w["seed"])
+    B = B or w["B"]
+    x = torch.randn(B, w["R"] + 1, w["K"], generator=g)
+    wt = torch.randn(w["N"], w["K"], generator=g) / w["K"] ** 0.5
+    return x, wt, 0.1 * torch.randn(w["N"], generator=g), torch.randn(B, w["R"], w["N"], generator=g)
+
+
+def proj_cpu(w, steps, budget_s=20.0):
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = w["B"]
+    Bs = min(B, 64)
+    x, wt, b, dy = (t.numpy() for t in proj_inputs(w, Bs))
+    ref_port.project_regions_step(x, wt, b, dy)
+    ts = []
+    t_end = time.perf_counter() + budget_s
+    while len(ts) < steps and (time.perf_counter() < t_end or len(ts) < 2):
+        t0 = time.perf_counter()
+        ref_port.project_regions_step(x, wt, b, dy)
+        ts.append(time.perf_counter() - t0)
+    t_sample = float(np.median(ts))
+    t_full = t_sample * (B / Bs)
+    return dict(value=B / t_full, unit="images/s", cores=cores, kind="port",
+                sample=(f"B={Bs} images x {w['R'] + 1} tokens, {w['K']}->{w['N']}, fp32, fwd+bwd, median of {len(ts)}; "
+                        + ("full size" if Bs == B else f"extrapolated to B={B} with time ~ B")),
+                measured_ms_per_sample_step=t_sample * 1e3, sample_batch=Bs), t_full
+
+
+def run_proj(args, w):
+    """One step = project_regions forward (y, normalised fp32 + fp16 copies, norms) + backward (dx, dW, db)."""
+    B, R, K, N = w["B"], w["R"], w["K"], w["N"]
+    cfgd = dict(workload=args.workload, description=w["desc"], B=B, R=R, K=K, N=N, in_dtype=w["in_dtype"])
+    if args.impl == "reference":
+        base, t_full = proj_cpu(w, args.steps)
+        print(json.dumps(dict(metric="project_regions_fwd_bwd_images_per_s", value=base["value"], unit="images/s",
+                              impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                              ms_per_step=t_full * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                              dtype="f32", data="synthetic", config=cfgd, cpu_baseline=base,
+                              e2e=dict(value=base["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return
+    pkg = importlib.import_module("t2i_clip-gan_b200")
+    torch.cuda.set_device(0)
+    dt = torch.bfloat16 if w["in_dtype"] == "bf16" else torch.float32
+    x_h, w_h, b_h, dy_h = proj_inputs(w)
+    x_h = x_h.to(dt).pin_memory()
+    wt = w_h.to(dt).cuda().requires_grad_(True)
+    bt = b_h.cuda().requires_grad_(True)
+    dy = dy_h.cuda().permute(0, 2, 1)
+    x = x_h.cuda().requires_grad_(True)
+    del dy_h
+
+    def step(xin):
+        feats = pkg.project_regions(xin, wt, bt)
+        feats.backward(dy)
+        return feats
+
+    def timed(fn, reps):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda") if x_h.numel() * x_h.element_size() < 200e6 else None
+    for _ in range(args.warmup):
+        x.grad = wt.grad = bt.grad = None
+        step(x)
+    torch.cuda.synchronize()
+    pkg._lib.reset_launch_count()
+    sampler = ClockSampler(0)
+    evs = []
+    for _ in range(args.steps):
+        x.grad = wt.grad = bt.grad = None
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(x)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    launches = pkg._lib.launch_count()
+    clocks = sampler.stop()
+    ms_step = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    out_pinned = torch.empty(N, dtype=torch.float32).pin_memory()
+    t0 = None
+    for it in range(args.steps + 2):
+        if it == 2:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        xin = x_h.to("cuda", non_blocking=True).requires_grad_(True)
+        bt.grad = None
+        step(xin)
+        out_pinned.copy_(bt.grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    # the forward kernel alone, with CUDA events: HBM-bound (three outputs: y fp32, vhat fp32, vhat fp16)
+    eng = pkg.get_engine("bf16")
+    with torch.no_grad():
+        xc, wc = x.detach().contiguous(), wt.detach().contiguous()
+        t_f = timed(lambda: eng.project_regions_fwd(xc, wc, bt.detach()), 5)
+    peaks = load_peaks()
+    es = x_h.element_size()
+    alg_bytes = B * (R + 1) * K * es + N * K * es + B * R * N * (4 + 4 + 2) + B * R * 8
+    gbs = alg_bytes / (t_f * 1e-3) / 1e9
+    flops = 2.0 * B * R * K * N
+    roof = dict(bound="hbm", achieved=gbs, peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"], traffic=None,
+                peak_source=peaks["src"], kernel="proj_l2norm_tc_kernel (forward)", fwd_ms=t_f,
+                fwd_tflops=flops / (t_f * 1e-3) / 1e12,
+                note="algorithmic bytes: read x and W once, write y (fp32), vhat (fp32), vhat (fp16), norms once")
+    base = None if args.no_cpu_baseline else proj_cpu(w, 5)[0]
+    print(json.dumps(dict(metric="project_regions_fwd_bwd_images_per_s", value=B / (ms_step * 1e-3), unit="images/s",
+                          n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True,
+                          scaling="weak", vs_baseline=None,
+                          dtype="bf16 operands / f32 accumulate" if dt == torch.bfloat16 else "tf32 / f32 accumulate",
+                          data="synthetic",
+                          config=dict(cfgd, l2=("L2 flushed (256 MiB memset) between timed iterations" if flush is not None
+                                                else "inputs larger than L2 (no flush)"),
+                                      step="project_regions forward + backward (dx, dW, db)"),
+                          clocks=clocks,
+                          e2e=dict(value=B / e2e_s, unit="images/s", ms_per_step=e2e_s * 1e3,
+                                   h2d_bytes_per_step=int(x_h.numel() * es), d2h_bytes_per_step=int(N * 4)),
+                          gpu_launches=launches, roofline=roof, cpu_baseline=base)))
+
+
 # --------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -418,9 +552,9 @@ def main():
     if args.steps is None:
         args.steps = 5 if w["B"] >= 1024 else 20
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if w.get("ntxent") or w.get("rmtok"):
+    if w.get("ntxent") or w.get("rmtok") or w.get("proj"):
         if int(os.environ.get("RANK", "0")) == 0:      # replicas only: small side operators, not sharded
-            (run_ntxent if w.get("ntxent") else run_rmtok)(args, w)
+            (run_ntxent if w.get("ntxent") else run_rmtok if w.get("rmtok") else run_proj)(args, w)
         return
 
     if args.impl == "reference":

@@ -167,6 +167,21 @@ DAMSM_API int damsm_ntxent_bwd_f32(const float *z, int64_t ldz, int64_t n2, int6
                          const float *sim, const float *nrm, const float *row_lse, const float *gout,
                          float *work, float *dz, void *stream);
 
+/* ---- region projection fused with the l2norm prologue (AddLinearOnCLIP.linear_subr: model.py:21,46,78,
+ * pretrain_DAMSM.py:350,359; CLS drop pretrain_DAMSM.py:125 / losses.py:350; l2norm losses.py:13-18,115) -----
+ * x (b, r+1, k) contiguous ViT hidden states (row 0 of every image = CLS), w (n, k) contiguous, bias (n) or NULL;
+ * dtype 0 = fp32 operands (run as TF32 on the tensor cores), 1 = bf16 operands (x and w).  16 <= n <= 512, n % 16 == 0.
+ * Outputs for the r region rows of every image (each may be NULL): y (b,r,n) fp32 = x.w^T + bias,
+ * xhat (b,r,n) fp32 = y/(|y|+1e-8), xhat16 (b,r,n) fp16, norm (b,r) = |y|, unorm (b,r) = |xhat|.
+ * Tensor-core precision: rel <= 2e-3 against the fp32 reference. */
+DAMSM_API int damsm_project_regions_fwd(const void *x, int dtype, int64_t b, int64_t r, int64_t k, const void *w,
+                              const float *bias, int64_t n, float *y, float *xhat, void *xhat16,
+                              float *norm, float *unorm, void *stream);
+/* dy (b,r,n) fp32 -> dx (b,r+1,k) [CLS rows zero], dw (n,k), db (n): all OVERWRITTEN, each may be NULL.
+ * x, w fp32; work: scratch of b*(r+1)*n floats.  Plain GEMMs (cuBLAS, TF32) + a column sum. */
+DAMSM_API int damsm_project_regions_bwd(const float *x, int64_t b, int64_t r, int64_t k, const float *w, int64_t n,
+                              const float *dy, float *work, float *dx, float *dw, float *db, void *stream);
+
 /* ---- rm_special_token (pretrain_DAMSM.py:58-79; called at :128-129 right before words_loss) ----------------
  * x (b,n,d) elements of elem_bytes (2 or 4), batch / token strides sb, sn in ELEMENTS, innermost dim contiguous;
  * mask (b,n) int64 with element strides msb, msn.  L_i = index of the first 0 of mask row i (n if none, clamped

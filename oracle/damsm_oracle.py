@@ -273,6 +273,25 @@ def nt_xent(z_i, z_j, temperature, g=1.0):
     return dict(loss=loss, sim=sim, dz_i=dz[:b], dz_j=dz[b:])
 
 
+# --------------------------------------------------------------------------- region projection
+def project_regions(subr, weight, bias=None, dy=None):
+    """AddLinearOnCLIP.linear_subr (nn.Linear(768, 512), model.py:21,46,78 / pretrain_DAMSM.py:350,359) followed by the
+    CLS drop of pretrain_DAMSM.py:125: y[b, r-1] = subr[b, r] . W^T + bias for r = 1..R.  Returns y (B, R, N); with
+    ``dy`` (B, R, N) also (dsubr (B, R+1, K) with zero CLS rows, dweight (N, K), dbias (N))."""
+    x = np.asarray(subr, np.float64)
+    w = np.asarray(weight, np.float64)
+    y = x[:, 1:, :] @ w.T
+    if bias is not None:
+        y = y + np.asarray(bias, np.float64)
+    if dy is None:
+        return y
+    g = np.asarray(dy, np.float64)
+    dx = np.zeros_like(x)
+    dx[:, 1:, :] = g @ w
+    dw = np.einsum("brn,brk->nk", g, x[:, 1:, :])
+    return y, dx, dw, g.sum(axis=(0, 1))
+
+
 # --------------------------------------------------------------------------- rm_special_token
 def rm_special_token(mask, words_emb):
     """pretrain_DAMSM.py:58-79.  Per caption: no 0 in the mask -> rows 1..n-2 (:67-69); else with e = index of the

@@ -150,3 +150,15 @@ def rm_special_token_step(mask, words_emb, dout):
     out = torch.stack(embs, dim=0)
     out.backward(torch.tensor(np.asarray(dout)))
     return out.detach().numpy(), torch.stack(masks, dim=0).numpy(), x.grad.numpy()
+
+
+def project_regions_step(subr, weight, bias, dy):
+    """linear_subr + CLS drop the way the reference runs it (model.py:46 / pretrain_DAMSM.py:359 then :125): nn.Linear on
+    the flattened tokens (CLS included), view back, slice, + autograd backward.  Returns (y, dsubr, dweight, dbias)."""
+    x = torch.tensor(np.asarray(subr), dtype=torch.float32, requires_grad=True)
+    w = torch.tensor(np.asarray(weight), dtype=torch.float32, requires_grad=True)
+    b = torch.tensor(np.asarray(bias), dtype=torch.float32, requires_grad=True)
+    bsz, _, k = x.shape
+    y = torch.nn.functional.linear(x.view(-1, k), w, b).view(bsz, -1, w.shape[0])[:, 1:, :]
+    y.backward(torch.tensor(np.asarray(dy), dtype=torch.float32))
+    return y.detach().numpy(), x.grad.numpy(), w.grad.numpy(), b.grad.numpy()

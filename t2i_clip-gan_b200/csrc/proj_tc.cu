@@ -1,0 +1,292 @@
+// Region projection fused with the l2norm prologue:
+//   y = subr . W^T + b        (AddLinearOnCLIP.linear_subr, model.py:21,46,78 / pretrain_DAMSM.py:350,359)
+//   drop the CLS row          (pretrain_DAMSM.py:125, losses.py:350)
+//   vhat = y / (|y| + 1e-8)   (l2norm, losses.py:13-18 as applied at :115)  -> fp32 copy, fp16 operand copy, norms
+// One tcgen05 GEMM whose accumulator row (N = 512 fp32 = all 512 TMEM columns) is normalised in the epilogue, so the
+// largest tensor of the loss is never re-read from HBM between the projection and the pair kernels.
+// X (B*(R+1), K) and W (N, K) are consumed in place by TMA: fp32 operands run as kind::tf32 (no conversion pass),
+// bf16 operands as kind::f16.  One CTA per 128 rows of X (CLS rows are computed and discarded: 1/(R+1) of the work).
+// Roofline: tensor; algorithmic flops 2*B*R*K*N.  The backward is three plain GEMMs (cuBLAS) + a column sum.
+#include <cublas_v2.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace damsm {
+using namespace tc;
+
+constexpr int PJ_THREADS = 192;     // warps 0-3: epilogue (one accumulator row per thread), 4: TMA, 5: MMA
+constexpr int PJ_STAGES = 2;
+constexpr uint32_t PJ_A_BYTES = 128 * 128;
+
+struct ProjParams {
+  int64_t rows_total;   // B * (R + 1)
+  int rp1, R, N, nkb;
+  const float *bias;    // (N) or NULL
+  float *y;             // (B, R, N) fp32 or NULL
+  float *xhat;          // (B, R, N) fp32 or NULL
+  __half *xhat16;       // (B, R, N) fp16 or NULL
+  float *norm, *unorm;  // (B, R) or NULL
+};
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               :
+               : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+template <bool TF32>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool acc) {
+  if constexpr (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)acc)
+        : "memory");
+  } else {
+    umma_f16(tmem_d, desc_a, desc_b, idesc, acc);
+  }
+}
+
+// kind::f16 / kind::tf32 instruction descriptor: fp32 accumulate, A/B format `fmt` (1 = BF16, 2 = TF32), K-major, M=128
+__host__ __device__ constexpr uint32_t pj_idesc(int fmt, int n) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+template <bool TF32>
+__global__ void __launch_bounds__(PJ_THREADS, 1)
+proj_l2norm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ProjParams p) {
+  constexpr int KB = TF32 ? 32 : 64;                 // elements per 128-byte operand row
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // W arrives as one or two boxes of up to 256 rows; a second box is always written (and counted) in full
+  const uint32_t b_bytes = (uint32_t)(p.N > 256 ? 512 : p.N) * 128;
+  const uint32_t stage_bytes = PJ_A_BYTES + b_bytes;
+  uint8_t *misc = smem + PJ_STAGES * stage_bytes;
+  uint64_t *full = reinterpret_cast<uint64_t *>(misc), *empty = full + PJ_STAGES, *d_full = empty + PJ_STAGES;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(d_full + 1);
+  float *sbias = reinterpret_cast<float *>(misc + 128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * 128;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PJ_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(d_full, 1);
+    fence_barrier_init();
+  }
+  for (int n = threadIdx.x; n < p.N; n += PJ_THREADS) sbias[n] = p.bias ? p.bias[n] : 0.f;
+  if (warp == 5) tmem_alloc<512>(tmem_ptr);
+  if (warp == 4 && lane == 0) { prefetch_tmap(&tmX); prefetch_tmap(&tmW); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int n1 = p.N > 256 ? 256 : p.N, n2 = p.N - n1;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        const int s = kb % PJ_STAGES;
+        mbar_wait(&empty[s], ((kb / PJ_STAGES) & 1) ^ 1);
+        uint8_t *a = smem + s * stage_bytes, *b = a + PJ_A_BYTES;
+        mbar_arrive_expect_tx(&full[s], stage_bytes);
+        tma_load_2d(a, &tmX, &full[s], kb * KB, (int)row0);          // rows past the tensor are zero-filled
+        tma_load_2d(b, &tmW, &full[s], kb * KB, 0);
+        if (n2 > 0) tma_load_2d(b + 256 * 128, &tmW, &full[s], kb * KB, 256);
+      }
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      const uint32_t id1 = pj_idesc(TF32 ? 2 : 1, n1), id2 = pj_idesc(TF32 ? 2 : 1, n2 > 0 ? n2 : 16);
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        const int s = kb % PJ_STAGES;
+        mbar_wait(&full[s], (kb / PJ_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t da = umma_desc_k_sw128(smem_u32(smem + s * stage_bytes));
+        const uint64_t db = umma_desc_k_sw128(smem_u32(smem + s * stage_bytes + PJ_A_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                                // 4 k-steps of 32 bytes per 128-byte row
+          umma_ss<TF32>(tmem_base, da + 2 * k, db + 2 * k, id1, (kb | k) != 0);
+          if (n2 > 0) umma_ss<TF32>(tmem_base + 256, da + 2 * k, db + ((256 * 128) >> 4) + 2 * k, id2, (kb | k) != 0);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(d_full);
+    }
+  } else {
+    // ---- epilogue: thread = accumulator row (TMEM lane); bias, |y|, then y / vhat / fp16 vhat / norms ----
+    const int64_t g = row0 + threadIdx.x;
+    const int r1 = (int)(g % p.rp1);
+    const bool valid = g < p.rows_total && r1 != 0;                 // r1 == 0 is the CLS row
+    const int64_t o = (g / p.rp1) * p.R + (r1 - 1);
+    mbar_wait(d_full, 0);
+    tc_fence_after();
+    const uint32_t t0 = tmem_base + (((uint32_t)warp * 32) << 16);
+    float ss = 0.f;
+    for (int c = 0; c < p.N; c += 16) {                               // warp-uniform: tcgen05.ld is collective
+      float x[16];
+      tmem_ld16(t0 + c, x);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { const float v = x[k] + sbias[c + k]; ss = fmaf(v, v, ss); }
+    }
+    const float nrm = sqrtf(ss), inv = 1.f / (nrm + kL2Eps);
+    float uu = 0.f;
+    for (int c = 0; c < p.N; c += 16) {
+      float x[16];
+      tmem_ld16(t0 + c, x);
+      float h[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { x[k] += sbias[c + k]; h[k] = x[k] * inv; uu = fmaf(h[k], h[k], uu); }
+      if (valid) {
+        if (p.y) {
+          float4 *q = reinterpret_cast<float4 *>(p.y + o * p.N + c);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) q[k] = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+        }
+        if (p.xhat) {
+          float4 *q = reinterpret_cast<float4 *>(p.xhat + o * p.N + c);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) q[k] = make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
+        }
+        if (p.xhat16) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const __half2 v = __floats2half2_rn(h[2 * k], h[2 * k + 1]);
+            pk[k] = *reinterpret_cast<const uint32_t *>(&v);
+          }
+          uint4 *q = reinterpret_cast<uint4 *>(p.xhat16 + o * p.N + c);
+          q[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          q[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+    }
+    if (valid) {
+      if (p.norm) p.norm[o] = nrm;
+      if (p.unorm) p.unorm[o] = sqrtf(uu);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<512>(tmem_base);
+}
+
+typedef CUresult (*PFN_encodeTiled2)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D row-major operand (rows, k) with `pitch` elements between rows; box = (box_rows, 128 bytes of k), 128B swizzle
+static int make_map_2d(CUtensorMap *m, const void *base, bool f32, uint64_t k, uint64_t rows, uint64_t pitch,
+                       uint32_t box_rows) {
+  static PFN_encodeTiled2 enc = nullptr;
+  if (!enc) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      enc = reinterpret_cast<PFN_encodeTiled2>(ptr);
+  }
+  DAMSM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  const uint32_t es = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {k, rows};
+  cuuint64_t strides[1] = {pitch * es};
+  cuuint32_t box[2] = {128 / es, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DAMSM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) k=%llu rows=%llu", (int)r, (unsigned long long)k,
+                (unsigned long long)rows);
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ x, int64_t rows, int n, float *__restrict__ out) {
+  // out[c] += sum over a slab of rows; grid.x = column blocks of 256, grid.y = row slabs
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= n) return;
+  const int64_t per = (rows + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  float s = 0.f;
+  for (int64_t r = r0; r < r1; ++r) s += x[r * n + c];
+  atomicAdd(out + c, s);
+}
+
+static cublasHandle_t pj_cublas() {
+  static thread_local cublasHandle_t h = nullptr;
+  if (!h && cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) h = nullptr;
+  return h;
+}
+
+}  // namespace damsm
+
+using namespace damsm;
+
+extern "C" int damsm_project_regions_fwd(const void *x, int dtype, int64_t b, int64_t r, int64_t k, const void *w,
+                                         const float *bias, int64_t n, float *y, float *xhat, void *xhat16,
+                                         float *norm, float *unorm, void *stream) {
+  DAMSM_REQUIRE(x && w, "project_regions_fwd: null pointer");
+  DAMSM_REQUIRE(dtype == 0 || dtype == 1, "project_regions_fwd: dtype %d (0 = fp32, 1 = bf16)", dtype);
+  DAMSM_REQUIRE(r >= 1 && n >= 16 && n <= 512 && n % 16 == 0, "project_regions_fwd: need 16 <= N <= 512, N %% 16 == 0 (got %lld)",
+                (long long)n);
+  const int es = dtype == 0 ? 4 : 2;
+  DAMSM_REQUIRE(k >= 1 && (k * es) % 16 == 0, "project_regions_fwd: K=%lld rows must be 16-byte multiples", (long long)k);
+  if (b == 0) return 0;
+  ProjParams p{};
+  p.rows_total = b * (r + 1); p.rp1 = (int)(r + 1); p.R = (int)r; p.N = (int)n;
+  const int kb = 128 / es;
+  p.nkb = (int)((k + kb - 1) / kb);
+  p.bias = bias; p.y = y; p.xhat = xhat; p.xhat16 = (__half *)xhat16; p.norm = norm; p.unorm = unorm;
+  DAMSM_REQUIRE(p.rows_total <= 2147483647LL - 128, "project_regions_fwd: too many rows");
+  CUtensorMap tmX, tmW;
+  int rc;
+  if ((rc = make_map_2d(&tmX, x, dtype == 0, (uint64_t)k, (uint64_t)p.rows_total, (uint64_t)k, 128))) return rc;
+  if ((rc = make_map_2d(&tmW, w, dtype == 0, (uint64_t)k, (uint64_t)n, (uint64_t)k, (uint32_t)(n > 256 ? 256 : n)))) return rc;
+  const uint32_t smem = PJ_STAGES * (PJ_A_BYTES + (uint32_t)(n > 256 ? 512 : n) * 128) + 128 + (uint32_t)n * 4 + 1024;
+  const unsigned grid = (unsigned)((p.rows_total + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == 0) {
+    DAMSM_CUDA(cudaFuncSetAttribute(proj_l2norm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    proj_l2norm_tc_kernel<true><<<grid, PJ_THREADS, smem, st>>>(tmX, tmW, p);
+  } else {
+    DAMSM_CUDA(cudaFuncSetAttribute(proj_l2norm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    proj_l2norm_tc_kernel<false><<<grid, PJ_THREADS, smem, st>>>(tmX, tmW, p);
+  }
+  return check_launch("project_regions_fwd");
+}
+
+// dy (B, R, N) fp32 -> dx (B, R+1, K) fp32 [OVERWRITTEN, CLS rows zero], dw (N, K) fp32 [OVERWRITTEN], db (N) [OVERWRITTEN];
+// each may be NULL.  work: B*(R+1)*N floats (dy re-laid with a zero CLS row per image, so that both gradient GEMMs
+// run over the contiguous (B*(R+1), .) matrices).  x, w fp32 (the wrapper up-casts bf16 operands once).
+extern "C" int damsm_project_regions_bwd(const float *x, int64_t b, int64_t r, int64_t k, const float *w, int64_t n,
+                                         const float *dy, float *work, float *dx, float *dw, float *db, void *stream) {
+  DAMSM_REQUIRE(x && w && dy && work, "project_regions_bwd: null pointer");
+  if (b == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  cublasHandle_t h = pj_cublas();
+  DAMSM_REQUIRE(h != nullptr, "project_regions_bwd: cublasCreate failed");
+  DAMSM_REQUIRE(cublasSetStream(h, st) == CUBLAS_STATUS_SUCCESS, "project_regions_bwd: cublasSetStream failed");
+  const float one = 1.f, zero = 0.f;
+  const int64_t rows = b * (r + 1);
+  const size_t pitch = sizeof(float) * (size_t)((r + 1) * n);
+  DAMSM_CUDA(cudaMemset2DAsync(work, pitch, 0, sizeof(float) * (size_t)n, (size_t)b, st));
+  DAMSM_CUDA(cudaMemcpy2DAsync(work + n, pitch, dy, sizeof(float) * (size_t)(r * n), sizeof(float) * (size_t)(r * n), (size_t)b,
+                               cudaMemcpyDeviceToDevice, st));
+  if (dx) {   // dx (rows x K) = work (rows x N) . w (N x K)      [row-major; cuBLAS sees the transposes]
+    cublasStatus_t s = cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)k, (int)rows, (int)n, &one, w, CUDA_R_32F, (int)k, work,
+                                    CUDA_R_32F, (int)n, &zero, dx, CUDA_R_32F, (int)k, CUBLAS_COMPUTE_32F_FAST_TF32,
+                                    CUBLAS_GEMM_DEFAULT_TENSOR_OP);
+    DAMSM_REQUIRE(s == CUBLAS_STATUS_SUCCESS, "project_regions_bwd: dx GEMM failed (%d)", (int)s);
+  }
+  if (dw) {   // dw (N x K) = work^T (N x rows) . x (rows x K)
+    cublasStatus_t s = cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, (int)k, (int)n, (int)rows, &one, x, CUDA_R_32F, (int)k, work,
+                                    CUDA_R_32F, (int)n, &zero, dw, CUDA_R_32F, (int)k, CUBLAS_COMPUTE_32F_FAST_TF32,
+                                    CUBLAS_GEMM_DEFAULT_TENSOR_OP);
+    DAMSM_REQUIRE(s == CUBLAS_STATUS_SUCCESS, "project_regions_bwd: dw GEMM failed (%d)", (int)s);
+  }
+  if (db) {
+    DAMSM_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * n, st));
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)(rows < 148 * 8 ? 1 : 148 * 4));
+    colsum_kernel<<<grid, 256, 0, st>>>(work, rows, (int)n, db);
+  }
+  return check_launch("project_regions_bwd");
+}

@@ -247,6 +247,37 @@ class CudaEngine:
                   dz.data_ptr(), _stream())
         return dz
 
+    # ---- region projection fused with the l2norm prologue (model.py:46,78) ----------------------------------------
+    def project_regions_fwd(self, x, w, bias):
+        """x (B, R+1, K) contiguous fp32 or bf16 (row 0 of every image = CLS), w (N, K) same dtype, bias (N) fp32 or
+        None.  Returns y (B,R,N) fp32, xhat, xhat16 (fp16), norm (B,R), unorm (B,R) -- what l2norm_fwd would give."""
+        _require_cuda(x, w, bias)
+        b, rp1, k = x.shape
+        n = w.shape[0]
+        r = rp1 - 1
+        dev = x.device
+        y = torch.empty((b, r, n), device=dev, dtype=torch.float32)
+        xhat = torch.empty((b, r, n), device=dev, dtype=torch.float32)
+        xhat16 = torch.empty((b, r, n), device=dev, dtype=torch.float16)
+        norm = torch.empty((b, r), device=dev, dtype=torch.float32)
+        unorm = torch.empty((b, r), device=dev, dtype=torch.float32)
+        _lib.call("damsm_project_regions_fwd", x.data_ptr(), 0 if x.dtype == torch.float32 else 1, b, r, k, w.data_ptr(),
+                  _lib.ptr(bias), n, y.data_ptr(), xhat.data_ptr(), xhat16.data_ptr(), norm.data_ptr(), unorm.data_ptr(),
+                  _stream())
+        return y, xhat, xhat16, norm, unorm
+
+    def project_regions_bwd(self, x32, w32, dy, need_dx=True, need_dw=True, need_db=True):
+        b, rp1, k = x32.shape
+        n = w32.shape[0]
+        dev = x32.device
+        work = torch.empty(b * rp1 * n, device=dev, dtype=torch.float32)
+        dx = torch.empty((b, rp1, k), device=dev, dtype=torch.float32) if need_dx else None
+        dw = torch.empty((n, k), device=dev, dtype=torch.float32) if need_dw else None
+        db = torch.empty(n, device=dev, dtype=torch.float32) if need_db else None
+        _lib.call("damsm_project_regions_bwd", x32.data_ptr(), b, rp1 - 1, k, w32.data_ptr(), n, dy.data_ptr(),
+                  work.data_ptr(), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _stream())
+        return dx, dw, db
+
     # ---- rm_special_token (pretrain_DAMSM.py:58-79) ------------------------------------------------------------
     def rm_special_token_fwd(self, x, mask_i64):
         """x (B,n,D) with a contiguous innermost dim, 2- or 4-byte elements; mask_i64 (B,n) int64."""

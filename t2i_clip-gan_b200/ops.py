@@ -12,10 +12,14 @@ from __future__ import annotations
 
 import math
 
+import warnings
+import weakref
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import _lib
 from .engine import get_engine
 
 DEFAULT_GAMMAS = (4.0, 5.0, 10.0)      # cfg/DAMSM/bird.yml:27-29, coco.yml:27-29, clip_bird_DMGAN.yml:25-28
@@ -66,6 +70,30 @@ def combine_column_lse(col_max: torch.Tensor, col_sum: torch.Tensor, group):
     return torch.log(s) + gmax
 
 
+# ----------------------------------------------------------------------------------------------- prologue cache
+# project_regions() already produces the normalised copies (fp32, fp16) and norms of its output in the GEMM epilogue.
+# They are remembered here, keyed by the output's storage, so that a following words_loss on that very tensor (any view
+# with the same layout, unmodified) skips its own l2norm pass over the largest tensor of the loss.
+_prologue = {}
+
+
+def _prologue_put(y, side):
+    for key in [k for k, (ref, _, _) in _prologue.items() if ref() is None]:
+        del _prologue[key]
+    _prologue[y.data_ptr()] = (weakref.ref(y), y._version, side)
+
+
+def _prologue_get(regions3):
+    hit = _prologue.get(regions3.data_ptr())
+    if hit is None:
+        return None
+    y = hit[0]()
+    if (y is None or regions3._version != hit[1] or regions3.shape != y.shape or regions3.stride() != y.stride()
+            or regions3.dtype != y.dtype):
+        return None
+    return hit[2]
+
+
 # ----------------------------------------------------------------------------------------------- words loss
 class DamsmWordsLoss(torch.autograd.Function):
     """words_loss (losses.py:219-272) for the local caption rows against all images."""
@@ -78,7 +106,11 @@ class DamsmWordsLoss(torch.autograd.Function):
             raise ValueError("words and regions must have the same (local) batch size")
         b_total, row_offset = bl * world, rank * bl
         qhat, qhat16, qnorm, qunorm = engine.l2norm_fwd(words3, want_bf16=engine.precision == "bf16", pad8=True)
-        vhat_l, vhat16_l, vnorm, _ = engine.l2norm_fwd(regions3, want_bf16=engine.precision == "bf16")
+        side = _prologue_get(regions3)
+        if side is not None:                     # regions come straight from project_regions(): already normalised
+            vhat_l, vhat16_l, vnorm = side[0], (side[1] if engine.precision == "bf16" else None), side[2]
+        else:
+            vhat_l, vhat16_l, vnorm, _ = engine.l2norm_fwd(regions3, want_bf16=engine.precision == "bf16")
         # image side: Gram matrices are computed for the local images only and gathered with the operands the
         # pair kernels read (fp32 path: vhat; tensor-core path: the fp16 copy)
         gram = _all_gather_rows(engine.gram(vhat_l), group)
@@ -189,10 +221,26 @@ def _class_ids_tensor(class_ids, b, device):
     return c
 
 
-def _pick_precision(precision, *tensors):
-    if precision is not None:
-        return precision
-    return "fp32"
+TC_SMEM_LIMIT = 232448      # 227 KB of shared memory per CTA on sm_100
+
+
+def tc_shape_supported(t, r, d):
+    """True when the tcgen05 path covers (T, R, D): T <= 128, R <= 255, D a multiple of 64 and the resident caption
+    tile + operand ring fit in shared memory (``damsm_words_tc_smem_bytes``)."""
+    need = _lib.load().damsm_words_tc_smem_bytes(int(t), int(r), int(d))
+    return 0 < need <= TC_SMEM_LIMIT
+
+
+def _pick_precision(precision, t, r, d):
+    if precision is None:
+        return "fp32"
+    if precision not in ("fp32", "bf16"):
+        raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+    if precision == "bf16" and not tc_shape_supported(t, r, d):
+        warnings.warn(f"words_loss: T={t}, R={r}, D={d} is outside the tensor-core kernel's range; "
+                      "using the exact fp32 CUDA path", RuntimeWarning, stacklevel=3)
+        return "fp32"
+    return precision
 
 
 def words_loss(region_features, words_embs, match_labels, cap_lens, class_ids, batch_size,
@@ -212,7 +260,7 @@ def words_loss(region_features, words_embs, match_labels, cap_lens, class_ids, b
         raise ValueError(f"batch_size={batch_size} does not match the tensors' batch {b}")
     if regions3.shape[2] != d:
         raise ValueError("words and regions must share the embedding size")
-    eng = engine or get_engine(_pick_precision(precision, words3, regions3))
+    eng = engine or get_engine(_pick_precision(precision, t, regions3.shape[1], d))
     dev = words3.device
     mask_u8 = _mask_to_u8(words_mask, cap_lens, b, t, dev)
     attn_maps = LazyAttnMaps(words3, regions3, mask_u8, eng)
@@ -333,6 +381,55 @@ def nt_xent(z_i, z_j, temperature, *, eps=1e-8, engine=None):
     out_dtype = z_i.dtype
     loss = DamsmNTXent.apply(z_i.float(), z_j.float(), 1.0 / float(temperature), float(eps), eng)
     return loss.to(out_dtype) if out_dtype != torch.float32 else loss
+
+
+# ----------------------------------------------------------------------------------------------- region projection
+class DamsmProjectRegions(torch.autograd.Function):
+    """linear_subr + CLS drop (model.py:46,78; pretrain_DAMSM.py:125) with the l2norm prologue of words_loss fused into
+    the GEMM epilogue.  Output: y (B, R, N) fp32."""
+
+    @staticmethod
+    def forward(ctx, subr, weight, bias, engine):
+        if subr.dtype == torch.bfloat16:
+            x, w = subr.contiguous(), weight.to(torch.bfloat16).contiguous()
+        else:
+            x, w = subr.float().contiguous(), weight.float().contiguous()
+        b32 = None if bias is None else bias.float().contiguous()
+        y, xhat, xhat16, norm, unorm = engine.project_regions_fwd(x, w, b32)
+        ctx.engine = engine
+        ctx.save_for_backward(x, w)
+        ctx.dtypes = (subr.dtype, weight.dtype, None if bias is None else bias.dtype)
+        _prologue_put(y, (xhat, xhat16, norm, unorm))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        dx, dw, db = ctx.engine.project_regions_bwd(x.float(), w.float(), dy.float().contiguous(), need[0], need[1],
+                                                    need[2] and ctx.dtypes[2] is not None)
+        dt = ctx.dtypes
+        return (None if dx is None else dx.to(dt[0]), None if dw is None else dw.to(dt[1]),
+                None if db is None else db.to(dt[2]), None)
+
+
+def project_regions(subr, weight, bias=None, *, engine=None):
+    """``linear_subr(subr.view(-1, K)).view(B, -1, N)[:, 1:, :].permute(0, 2, 1)`` (model.py:46 / pretrain_DAMSM.py:359
+    followed by :125): ``subr`` (B, R+1, K) ViT hidden states with the CLS token in row 0, ``weight`` (N, K), ``bias``
+    (N).  Returns ``region_features`` (B, N, R) -- the tensor ``words_loss`` takes -- computed on the tensor cores
+    (fp32 operands as TF32, bf16 operands as bf16; fp32 accumulate, fp32 result).  A ``words_loss`` call on the result
+    reuses the normalised copies made in the GEMM epilogue."""
+    if subr.dim() != 3 or weight.dim() != 2 or weight.shape[1] != subr.shape[2]:
+        raise ValueError("project_regions: subr must be (B, R+1, K) and weight (N, K)")
+    if subr.shape[1] < 2:
+        raise ValueError("project_regions: need the CLS row plus at least one region")
+    n = weight.shape[0]
+    if n % 16 or not 16 <= n <= 512:
+        raise ValueError("project_regions: N must be a multiple of 16 in [16, 512]")
+    if bias is not None and bias.shape != (n,):
+        raise ValueError("project_regions: bias must be (N,)")
+    eng = engine or get_engine("bf16")
+    return DamsmProjectRegions.apply(subr, weight, bias, eng).permute(0, 2, 1)
 
 
 # ----------------------------------------------------------------------------------------------- rm_special_token

@@ -79,3 +79,14 @@ def test_reference_import_lines_work():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
     assert out.returncode == 0, out.stderr
     assert out.stdout.split()[0] == "10.0"
+
+
+def test_tensor_core_shape_query_is_a_host_function():
+    """damsm_words_tc_smem_bytes needs no GPU: the wrapper uses it to route unsupported shapes to the exact path."""
+    import importlib
+    pkg = importlib.import_module("t2i_clip-gan_b200")
+    assert pkg.ops.tc_shape_supported(77, 196, 512) and pkg.ops.tc_shape_supported(18, 49, 512)
+    for bad in ((129, 49, 512), (77, 256, 512), (18, 49, 500), (100, 196, 512)):
+        assert not pkg.ops.tc_shape_supported(*bad), bad
+    with __import__("pytest").raises(ValueError):
+        pkg.ops._pick_precision("fp16", 18, 49, 512)

@@ -110,3 +110,20 @@ def test_tc_one_sided_gradients(side):
         assert w.grad is None and rel(r.grad.cpu().numpy(), o["dregions"]) <= TOL
     else:
         assert r.grad is None and rel(w.grad.cpu().numpy(), o["dwords"]) <= TOL
+
+
+def test_tc_unsupported_shape_falls_back_to_exact_cuda_path():
+    """T=100 with R=100 does not fit the tensor-core kernel's shared memory (128-word tile resident): precision='bf16'
+    then runs the exact fp32 CUDA kernels (a warning says so) -- still on the GPU, never on the CPU."""
+    B, T, R = 3, 100, 100
+    assert not pkg.ops.tc_shape_supported(T, R, 512) and pkg.ops.tc_shape_supported(77, R, 512)
+    x = rounded(O.make_inputs(B, T, R, seed=41, class_ids=False))
+    o = O.words_loss(x["words"], x["regions"], x["mask"], x["labels"], None, 4.0, 5.0, 10.0)
+    w = torch.tensor(x["words"], device="cuda").requires_grad_(True)
+    r = torch.tensor(x["regions"], device="cuda").requires_grad_(True)
+    with pytest.warns(RuntimeWarning, match="exact fp32 CUDA path"):
+        l0, l1, _ = pkg.words_loss(r.permute(0, 2, 1), w.permute(0, 2, 1), torch.arange(B, device="cuda"), None, None, B,
+                                   torch.tensor(x["mask"]), 4.0, 5.0, 10.0, precision="bf16")
+    (l0 + l1).backward()
+    assert abs(l0.item() - o["loss0"]) <= 1e-5 * max(1, abs(o["loss0"]))
+    assert rel(w.grad.cpu().numpy(), o["dwords"]) <= 1e-5 and rel(r.grad.cpu().numpy(), o["dregions"]) <= 1e-5
