@@ -167,6 +167,12 @@ DAMSM_API int damsm_ntxent_bwd_f32(const float *z, int64_t ldz, int64_t n2, int6
                          const float *sim, const float *nrm, const float *row_lse, const float *gout,
                          float *work, float *dz, void *stream);
 
+/* ---- R-precision scoring (trainer.py:587-603): img (b,d) rows ldi apart; cand (b,c,d) with element strides
+ * csb, csc (innermost contiguous), candidate 0 = the true caption.  scores (b,c) (may be NULL) =
+ * img_i.cand_ic / max(|img_i||cand_ic|, eps); hit (b) int32 = 1 where argmax_c == 0 (first maximum). */
+DAMSM_API int damsm_rprecision_f32(const float *img, int64_t ldi, const float *cand, int64_t csb, int64_t csc,
+                         int64_t b, int64_t c, int64_t d, float eps, float *scores, int32_t *hit, void *stream);
+
 /* ---- region projection fused with the l2norm prologue (AddLinearOnCLIP.linear_subr: model.py:21,46,78,
  * pretrain_DAMSM.py:350,359; CLS drop pretrain_DAMSM.py:125 / losses.py:350; l2norm losses.py:13-18,115) -----
  * x (b, r+1, k) contiguous ViT hidden states (row 0 of every image = CLS), w (n, k) contiguous, bias (n) or NULL;

@@ -273,6 +273,19 @@ def nt_xent(z_i, z_j, temperature, g=1.0):
     return dict(loss=loss, sim=sim, dz_i=dz[:b], dz_j=dz[b:])
 
 
+# --------------------------------------------------------------------------- R-precision
+def r_precision_scores(img_code, sent_codes, eps=1e-8):
+    """trainer.py:587-603 for every image of the batch: scores = img . sent^T (:596), norm = |img| |sent| (:597-599),
+    scores0 = scores / clamp(norm, min=1e-8) (:600), hit = argmax(scores0) == 0 (:601).  sent_codes (B, C, D), true
+    caption first.  Returns (scores0 (B, C), hit (B,) bool)."""
+    a = np.asarray(img_code, np.float64)
+    c = np.asarray(sent_codes, np.float64)
+    dots = np.einsum("bd,bcd->bc", a, c)
+    nrm = np.sqrt((a * a).sum(-1))[:, None] * np.sqrt((c * c).sum(-1))
+    s0 = dots / np.maximum(nrm, eps)
+    return s0, s0.argmax(axis=1) == 0
+
+
 # --------------------------------------------------------------------------- region projection
 def project_regions(subr, weight, bias=None, dy=None):
     """AddLinearOnCLIP.linear_subr (nn.Linear(768, 512), model.py:21,46,78 / pretrain_DAMSM.py:350,359) followed by the

@@ -162,3 +162,19 @@ def project_regions_step(subr, weight, bias, dy):
     y = torch.nn.functional.linear(x.view(-1, k), w, b).view(bsz, -1, w.shape[0])[:, 1:, :]
     y.backward(torch.tensor(np.asarray(dy), dtype=torch.float32))
     return y.detach().numpy(), x.grad.numpy(), w.grad.numpy(), b.grad.numpy()
+
+
+def r_precision_step(img_code, sent_codes):
+    """R-precision scoring the way the reference runs it (trainer.py:587-603): a Python loop over the batch, per image a
+    1 x C torch.mm, two torch.norm calls, a 1 x C product of norms clamped at 1e-8, argmax.  Returns (scores0, hit)."""
+    img = torch.tensor(np.asarray(img_code), dtype=torch.float32)
+    cands = torch.tensor(np.asarray(sent_codes), dtype=torch.float32)
+    out, hits = [], []
+    for i in range(img.shape[0]):
+        one = img[i].unsqueeze(0)
+        sc = torch.mm(one, cands[i].t())
+        nrm = torch.mm(torch.norm(one, 2, dim=1, keepdim=True), torch.norm(cands[i], 2, dim=1, keepdim=True).t())
+        s0 = sc / nrm.clamp(min=1e-8)
+        out.append(s0[0])
+        hits.append(bool(torch.argmax(s0) == 0))
+    return torch.stack(out).numpy(), np.array(hits)

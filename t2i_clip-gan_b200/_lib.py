@@ -42,6 +42,7 @@ SIGNATURES = {
                                  _p, _p, _p, _p],
     "damsm_ntxent_fwd_f32": [_p, _l, _l, _l, _f, _f, _p, _p, _p, _p, _p],
     "damsm_ntxent_bwd_f32": [_p, _l, _l, _l, _f, _f, _p, _p, _p, _p, _p, _p, _p],
+    "damsm_rprecision_f32": [_p, _l, _p, _l, _l, _l, _l, _l, _f, _p, _p, _p],
     "damsm_project_regions_fwd": [_p, _i, _l, _l, _l, _p, _p, _l, _p, _p, _p, _p, _p, _p],
     "damsm_project_regions_bwd": [_p, _l, _l, _l, _p, _l, _p, _p, _p, _p, _p, _p],
     "damsm_rm_special_token_fwd": [_p, _l, _l, _l, _l, _l, _l, _p, _l, _l, _p, _p, _p],
@@ -61,7 +62,7 @@ LAUNCHES = {
     "damsm_cos_logits_f32": 4, "damsm_cos_logits_bwd_f32": 5,
     "damsm_ntxent_fwd_f32": 3, "damsm_ntxent_bwd_f32": 4,
     "damsm_rm_special_token_fwd": 1, "damsm_rm_special_token_bwd": 1,
-    "damsm_project_regions_fwd": 1, "damsm_project_regions_bwd": 1,
+    "damsm_project_regions_fwd": 1, "damsm_project_regions_bwd": 1, "damsm_rprecision_f32": 1,
     "damsm_func_attention_fwd_f32": 1, "damsm_func_attention_bwd_f32": 1,
 }
 _launches = 0

@@ -158,6 +158,48 @@ __global__ void __launch_bounds__(256) ntxent_bwd_coef_kernel(const float *__res
   if ((threadIdx.x & 31) == 0 && racc != 0.f) atomicAdd(coef + a, racc);
 }
 
+// ------------------------------------------------------------------------------------- R-precision (trainer.py:587-603)
+// Per generated image i: scores0[c] = img_i . cand_ic / max(|img_i| |cand_ic|, eps) over C candidate captions (the
+// true one first, then 99 mismatched); the image counts as a hit when argmax == 0 (first maximum, as torch.argmax).
+// The reference runs this as a Python loop of 1 x 100 torch.mm calls; here one CTA per image, one warp per candidate.
+__global__ void __launch_bounds__(256) rprecision_kernel(const float *__restrict__ img, int64_t ldi,
+                                                         const float *__restrict__ cand, int64_t csb, int64_t csc,
+                                                         int c, int d, float eps, float *__restrict__ scores,
+                                                         int *__restrict__ hit) {
+  extern __shared__ float sc[];                      // c scores
+  const int i = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float *a = img + (int64_t)i * ldi;
+  float na = 0.f;
+  for (int k = lane; k < d; k += 32) na = fmaf(a[k], a[k], na);
+  na = sqrtf(warp_sum(na));
+  for (int j = warp; j < c; j += (int)(blockDim.x >> 5)) {
+    const float *b = cand + (int64_t)i * csb + (int64_t)j * csc;
+    float dot = 0.f, nb = 0.f;
+    for (int k = lane; k < d; k += 32) { const float v = b[k]; dot = fmaf(a[k], v, dot); nb = fmaf(v, v, nb); }
+    dot = warp_sum(dot);
+    nb = sqrtf(warp_sum(nb));
+    if (lane == 0) {
+      const float s = dot / fmaxf(na * nb, eps);
+      sc[j] = s;
+      if (scores) scores[(int64_t)i * c + j] = s;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float best = -INFINITY;
+    int arg = 0x7fffffff;
+    for (int j = lane; j < c; j += 32)
+      if (sc[j] > best) { best = sc[j]; arg = j; }    // strict: keeps the first maximum of this lane's stride
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if (lane == 0) hit[i] = (arg == 0) ? 1 : 0;
+  }
+}
+
 }  // namespace damsm
 
 using namespace damsm;
@@ -260,4 +302,14 @@ extern "C" int damsm_ntxent_bwd_f32(const float *z, int64_t ldz, int64_t n2, int
   if (rc) return rc;
   norm_term_kernel<<<(unsigned)((n2 * d + 255) / 256), 256, 0, st>>>(dz, z, ldz, coef, nrm, (int)n2, (int)d);
   return check_launch("ntxent_bwd");
+}
+
+extern "C" int damsm_rprecision_f32(const float *img, int64_t ldi, const float *cand, int64_t csb, int64_t csc, int64_t b,
+                                    int64_t c, int64_t d, float eps, float *scores, int32_t *hit, void *stream) {
+  DAMSM_REQUIRE(img && cand && hit, "rprecision: null pointer");
+  DAMSM_REQUIRE(c >= 1 && c <= 8192 && d >= 1, "rprecision: bad shape C=%lld D=%lld", (long long)c, (long long)d);
+  if (b == 0) return 0;
+  rprecision_kernel<<<(unsigned)b, 256, sizeof(float) * c, (cudaStream_t)stream>>>(img, ldi, cand, csb, csc, (int)c, (int)d,
+                                                                                 eps, scores, hit);
+  return check_launch("rprecision");
 }

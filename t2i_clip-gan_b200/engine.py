@@ -247,6 +247,16 @@ class CudaEngine:
                   dz.data_ptr(), _stream())
         return dz
 
+    # ---- R-precision scoring (trainer.py:587-603) ---------------------------------------------------------------
+    def rprecision(self, img, cand, eps):
+        _require_cuda(img, cand)
+        b, c, d = cand.shape
+        scores = torch.empty((b, c), device=img.device, dtype=torch.float32)
+        hit = torch.empty(b, device=img.device, dtype=torch.int32)
+        _lib.call("damsm_rprecision_f32", img.data_ptr(), img.stride(0), cand.data_ptr(), cand.stride(0), cand.stride(1),
+                  b, c, d, float(eps), scores.data_ptr(), hit.data_ptr(), _stream())
+        return scores, hit
+
     # ---- region projection fused with the l2norm prologue (model.py:46,78) ----------------------------------------
     def project_regions_fwd(self, x, w, bias):
         """x (B, R+1, K) contiguous fp32 or bf16 (row 0 of every image = CLS), w (N, K) same dtype, bias (N) fp32 or

@@ -383,6 +383,24 @@ def nt_xent(z_i, z_j, temperature, *, eps=1e-8, engine=None):
     return loss.to(out_dtype) if out_dtype != torch.float32 else loss
 
 
+# ----------------------------------------------------------------------------------------------- R-precision
+def r_precision_scores(img_code, sent_codes, eps=1e-8, *, engine=None):
+    """The R-precision test of trainer.py:587-603 for a whole batch: ``img_code`` (B, D) generated-image codes,
+    ``sent_codes`` (B, C, D) candidate sentence codes per image with the TRUE caption at index 0 (the reference
+    concatenates it in front of 99 mismatched ones, :593).  Returns ``(scores0 (B, C), hit (B,) bool)`` with
+    ``scores0 = img.sent / max(|img||sent|, eps)`` (:596-600) and ``hit = argmax(scores0) == 0`` (:601).  No gradient."""
+    if img_code.dim() != 2 or sent_codes.dim() != 3 or sent_codes.shape[0] != img_code.shape[0] \
+            or sent_codes.shape[2] != img_code.shape[1]:
+        raise ValueError("r_precision_scores: img_code must be (B, D) and sent_codes (B, C, D)")
+    eng = engine or get_engine("fp32")
+    img = img_code.detach().float()
+    cand = sent_codes.detach().float()
+    img = img if img.stride(1) == 1 else img.contiguous()
+    cand = cand if cand.stride(2) == 1 else cand.contiguous()
+    scores, hit = eng.rprecision(img, cand, eps)
+    return scores, hit.bool()
+
+
 # ----------------------------------------------------------------------------------------------- region projection
 class DamsmProjectRegions(torch.autograd.Function):
     """linear_subr + CLS drop (model.py:46,78; pretrain_DAMSM.py:125) with the l2norm prologue of words_loss fused into
