@@ -31,6 +31,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 struct TcLayout {
   int rs;            // operand rows fetched per stage (ceil8(R+1))
+  int rs_half;       // cluster mode: rows [0, rs_half) are fetched by CTA 0, the rest by CTA 1 (rs_half % 8 == 0)
   int tiles;         // M tiles of 128 region rows
   int k2_steps;      // K=16 steps of GEMM2 (ceil16(R)/16)
   int nkb_d, nkb_r;  // 64-wide k-blocks of GEMM1 / GEMM2
@@ -42,6 +43,7 @@ struct TcLayout {
 __host__ __device__ inline TcLayout tc_layout(int NT, int R, int D) {
   TcLayout l;
   l.rs = (R + 1 + 7) & ~7;
+  l.rs_half = ((l.rs / 2) + 7) & ~7;
   l.tiles = (R + 1 + 127) / 128;
   l.k2_steps = (R + 15) / 16;
   l.nkb_d = D / 64;
@@ -179,10 +181,14 @@ __device__ __forceinline__ float warp_colsum(float (&v)[N], int lane) {
 
 // NW = 16: the two softmax warps that own no region row (R+1 <= 224) serve as TMA producer (warp 7) and MMA
 // issuer (warp 15), 4 warps per scheduler and 128 registers per thread; NW = 18: two extra warps take those roles.
-template <int NT, bool BWD, int NW>
+// CL = 2: the CTAs of captions 2k and 2k+1 form a cluster and walk the same image sequence; each fetches one half of
+// the rows of every vhat / Gx stage and multicasts it to both (half the L2 reads per pair), a ring slot is released
+// when both CTAs have multiplied it.
+template <int NT, bool BWD, int NW, int CL>
 __global__ void __launch_bounds__(NW * 32, 1)
 words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
-                const __grid_constant__ CUtensorMap tmG, TcParams p) {
+                const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmV2,
+                const __grid_constant__ CUtensorMap tmG2, TcParams p) {
   constexpr int NH = NT / 2;                 // words per softmax thread
   constexpr int TC_THREADS = NW * 32;
   constexpr int TMA_WARP = (NW == 16) ? 7 : 16;
@@ -223,7 +229,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   for (uint32_t o = threadIdx.x * 16; o < L.misc_off; o += TC_THREADS * 16)
     *reinterpret_cast<uint4 *>(smem + o) = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
     mbar_init(q_full, 1); mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(m_full, 1);
     // the softmax warps arrive once per warp (lane 0 after __syncwarp): 448 per-thread arrivals on one shared-memory
     // word serialise and were the longest item of the per-pair critical path
@@ -242,11 +248,16 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int k = 0; k < 24; ++k) red1[t * 24 + k] = red2[t * 24 + k] = 0.f;   // [3][NT][8]: unused warp slots stay 0
   }
   if (warp == MMA_WARP) tmem_alloc<512>(tmem_ptr);
-  if (warp == TMA_WARP && lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmV); prefetch_tmap(&tmG); }
+  if (warp == TMA_WARP && lane == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmV); prefetch_tmap(&tmG);
+    if constexpr (CL == 2) { prefetch_tmap(&tmV2); prefetch_tmap(&tmG2); }
+  }
   fence_proxy_async_smem();           // the zero fill must be ordered before the TMA / MMA (async proxy) accesses
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) cluster_sync();   // the peer multicasts into this CTA's stages and arrives on its barriers
   tc_fence_after();
+  const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t idesc = umma_idesc_f16(NT);
   const uint32_t col_m = (uint32_t)(nbuf * L.tiles * NT);     // TMEM column of M'
@@ -263,8 +274,14 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (DBG(p, 8) && m == &tmG) { mbar_arrive(&full[stage]); }          // timing experiments only
           else if (DBG(p, 16) && m == &tmV) { mbar_arrive(&full[stage]); }
           else {
-          mbar_arrive_expect_tx(&full[stage], (uint32_t)L.rs * 128);
-          tma_load_3d(stages + stage * L.stage_bytes, m, &full[stage], kb * 64, 0, j);
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)L.rs * 128);      // both halves land here
+          if constexpr (CL == 2) {
+            const int r0 = crank ? L.rs_half : 0;
+            const CUtensorMap *mh = crank ? (m == &tmV ? &tmV2 : &tmG2) : m;
+            tma_load_3d_mc(stages + stage * L.stage_bytes + r0 * 128, mh, &full[stage], kb * 64, r0, j, (uint16_t)3);
+          } else {
+            tma_load_3d(stages + stage * L.stage_bytes, m, &full[stage], kb * 64, 0, j);
+          }
           }
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -312,6 +329,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           }
           if (DBG(p, 128)) mbar_arrive(&empty[stage]); else
+          if constexpr (CL == 2) umma_commit_mc(&empty[stage], (uint16_t)3); else
           umma_commit(&empty[stage]);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -341,6 +359,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           left -= nk;
           if (DBG(p, 128)) mbar_arrive(&empty[stage]); else
+          if constexpr (CL == 2) umma_commit_mc(&empty[stage], (uint16_t)3); else
           umma_commit(&empty[stage]);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -696,6 +715,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) cluster_sync();   // no CTA may leave while its peer can still signal its barriers
   if (warp == MMA_WARP) tmem_dealloc<512>(tmem_base);
 }
 
@@ -757,8 +777,9 @@ __global__ void __launch_bounds__(256) gram_pack_f16_kernel(const float *__restr
 struct TcLaunch {
   int nt;
   TcLayout L;
-  CUtensorMap tmQ, tmV, tmG;
+  CUtensorMap tmQ, tmV, tmG, tmV2, tmG2, tmVh, tmGh;   // full-row boxes; cluster mode: second / first half-row boxes
   int sms;
+  bool cluster_ok;
 };
 
 static int tc_prepare(TcLaunch *tl, const char *who, const void *qhat16, int64_t q_rows, const void *vhat16,
@@ -780,6 +801,18 @@ static int tc_prepare(TcLaunch *tl, const char *who, const void *qhat16, int64_t
   if ((rc = make_map_f16(&tl->tmQ, qhat16, d, q_rows, br, d, q_rows * d, tl->nt))) return rc;
   if ((rc = make_map_f16(&tl->tmV, vhat16, d, r, bc, d, r * d, tl->L.rs))) return rc;
   if ((rc = make_map_f16(&tl->tmG, gx, rk, r + 1, bc, rk, (r + 1) * rk, tl->L.rs))) return rc;
+  // cluster mode (pairs of captions share the image stream): half-row boxes for the two CTAs of a cluster
+  tl->tmV2 = tl->tmV; tl->tmG2 = tl->tmG;
+  tl->cluster_ok = tl->nt == 80 && tl->L.act_warps <= 14 && tl->L.rs - tl->L.rs_half >= 8 && !getenv("DAMSM_TC_NO_CLUSTER");
+  if (tl->cluster_ok) {
+    CUtensorMap a, b;
+    const uint32_t h0 = (uint32_t)tl->L.rs_half, h1 = (uint32_t)(tl->L.rs - tl->L.rs_half);
+    if ((rc = make_map_f16(&a, vhat16, d, r, bc, d, r * d, h0))) return rc;
+    if ((rc = make_map_f16(&tl->tmV2, vhat16, d, r, bc, d, r * d, h1))) return rc;
+    if ((rc = make_map_f16(&b, gx, rk, r + 1, bc, rk, (r + 1) * rk, h0))) return rc;
+    if ((rc = make_map_f16(&tl->tmG2, gx, rk, r + 1, bc, rk, (r + 1) * rk, h1))) return rc;
+    tl->tmVh = a; tl->tmGh = b;
+  }
   return 0;
 }
 
@@ -796,15 +829,28 @@ static int tc_launch(const TcLaunch &tl, TcParams &p, int64_t rows, cudaStream_t
 #define DAMSM_LAUNCH_TC(NT_)                                                                                          \
   do {                                                                                                                \
     if (tl.L.act_warps <= 14) {                                                                                       \
-      DAMSM_CUDA(cudaFuncSetAttribute(words_tc_kernel<NT_, BWD, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+      DAMSM_CUDA(cudaFuncSetAttribute(words_tc_kernel<NT_, BWD, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)tl.L.total));                                                              \
-      words_tc_kernel<NT_, BWD, 16><<<grid, 16 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, p);                    \
+      words_tc_kernel<NT_, BWD, 16, 1><<<grid, 16 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, tl.tmV, tl.tmG, p); \
     } else {                                                                                                          \
-      DAMSM_CUDA(cudaFuncSetAttribute(words_tc_kernel<NT_, BWD, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+      DAMSM_CUDA(cudaFuncSetAttribute(words_tc_kernel<NT_, BWD, 18, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)tl.L.total));                                                              \
-      words_tc_kernel<NT_, BWD, 18><<<grid, 18 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, p);                    \
+      words_tc_kernel<NT_, BWD, 18, 1><<<grid, 18 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, tl.tmV, tl.tmG, p); \
     }                                                                                                                 \
   } while (0)
+  if (tl.cluster_ok && rows % 2 == 0) {
+    // pairs of caption rows as 2-CTA clusters sharing the image stream by TMA multicast
+    auto kern = words_tc_kernel<80, BWD, 16, 2>;
+    DAMSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.L.total));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(16 * 32); cfg.dynamicSmemBytes = tl.L.total; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    DAMSM_CUDA(cudaLaunchKernelEx(&cfg, kern, tl.tmQ, tl.tmVh, tl.tmGh, tl.tmV2, tl.tmG2, p));
+    return check_launch(BWD ? "words_bwd_tc (fused recompute, 2-CTA clusters)" : "words_fwd_tc (2-CTA clusters)");
+  }
   switch (tl.nt) {
     case 32: DAMSM_LAUNCH_TC(32); break;
     case 64: DAMSM_LAUNCH_TC(64); break;
@@ -915,6 +961,7 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
   DAMSM_REQUIRE(chunk >= 1, "words_bwd_tc: workspace of %lld B is smaller than one caption row (%lld B)",
                 (long long)workspace_bytes, (long long)row_bytes);
   if (chunk > br) chunk = br;
+  if (chunk > 2 && (chunk & 1)) --chunk;      // even chunks: pairs of caption rows run as 2-CTA clusters
   cudaStream_t st = (cudaStream_t)stream;
   cublasHandle_t h = get_cublas();
   DAMSM_REQUIRE(h != nullptr, "words_bwd_tc: cublasCreate failed");
