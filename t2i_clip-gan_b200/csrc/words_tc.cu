@@ -838,7 +838,9 @@ static int tc_launch(const TcLaunch &tl, TcParams &p, int64_t rows, cudaStream_t
       words_tc_kernel<NT_, BWD, 18, 1><<<grid, 18 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, tl.tmV, tl.tmG, p); \
     }                                                                                                                 \
   } while (0)
-  if (tl.cluster_ok && rows % 2 == 0) {
+  // forward: always when possible; backward: opt-in (DAMSM_TC_CLUSTER_BWD=1) -- its kernel is bound by the softmax
+  // warps, not by the image stream, and the lock-step of the two CTAs costs it ~1 % (measured at C5)
+  if (tl.cluster_ok && rows % 2 == 0 && (!BWD || getenv("DAMSM_TC_CLUSTER_BWD"))) {
     // pairs of caption rows as 2-CTA clusters sharing the image stream by TMA multicast
     auto kern = words_tc_kernel<80, BWD, 16, 2>;
     DAMSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.L.total));

@@ -127,3 +127,24 @@ def test_tc_unsupported_shape_falls_back_to_exact_cuda_path():
     (l0 + l1).backward()
     assert abs(l0.item() - o["loss0"]) <= 1e-5 * max(1, abs(o["loss0"]))
     assert rel(w.grad.cpu().numpy(), o["dwords"]) <= 1e-5 and rel(r.grad.cpu().numpy(), o["dregions"]) <= 1e-5
+
+
+@pytest.mark.parametrize("mode", ["fwd_clusters", "bwd_clusters_too", "no_clusters"])
+def test_tc_cluster_modes_agree(mode, monkeypatch):
+    """2-CTA clusters sharing the image stream by TMA multicast (default: forward only; DAMSM_TC_CLUSTER_BWD=1 adds the
+    backward; DAMSM_TC_NO_CLUSTER=1 disables them): every mode meets the parity bar on the same inputs."""
+    if mode == "bwd_clusters_too":
+        monkeypatch.setenv("DAMSM_TC_CLUSTER_BWD", "1")
+    if mode == "no_clusters":
+        monkeypatch.setenv("DAMSM_TC_NO_CLUSTER", "1")
+    B, T, R = 10, 77, 196
+    x = rounded(O.make_inputs(B, T, R, seed=51, class_ids=True, n_classes=4))
+    o = O.words_loss(x["words"], x["regions"], x["mask"], x["labels"], x["class_ids"], 4.0, 5.0, 10.0)
+    w = torch.tensor(x["words"], device="cuda").requires_grad_(True)
+    r = torch.tensor(x["regions"], device="cuda").requires_grad_(True)
+    l0, l1, _ = pkg.words_loss(r.permute(0, 2, 1), w.permute(0, 2, 1), torch.arange(B, device="cuda"), None,
+                               x["class_ids"], B, torch.tensor(x["mask"]), 4.0, 5.0, 10.0, precision="bf16")
+    (l0 + l1).backward()
+    assert abs(l0.item() - o["loss0"]) <= TOL * max(1, abs(o["loss0"]))
+    assert abs(l1.item() - o["loss1"]) <= TOL * max(1, abs(o["loss1"]))
+    assert rel(w.grad.cpu().numpy(), o["dwords"]) <= TOL and rel(r.grad.cpu().numpy(), o["dregions"]) <= TOL
