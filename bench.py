@@ -34,6 +34,8 @@ D = 512
 WORKLOADS = {
     "c1": dict(B=48, T=18, R=49, cls=True, precision="fp32", seed=2026, desc="CUB bird DAMSM shape"),
     "c2": dict(B=48, T=18, R=49, cls=False, precision="fp32", seed=2027, desc="COCO DAMSM shape, class mask off"),
+    "t28": dict(B=48, T=28, R=49, cls=True, precision="fp32", seed=2037,
+                desc="reference-actual caption length (words_num=30 minus SOS/EOS, pretrain_DAMSM.py:103)"),
     "c3": dict(B=10, T=77, R=49, cls=True, precision="fp32", seed=2028, desc="DM-GAN generator-step DAMSM term"),
     "c4": dict(B=1024, T=77, R=196, cls=False, precision="bf16", seed=2029, desc="large-batch fine-tune, ViT-B/16"),
     "c5": dict(B=4096, T=77, R=196, cls=False, precision="bf16", seed=2030, desc="scaling sweep, ViT-B/16, bf16 in"),
