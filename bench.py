@@ -28,6 +28,27 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+# Only the result line may reach stdout: libraries print there too (NCCL's version banner under torchrun).  File
+# descriptor 1 is pointed at stderr for the whole run and the JSON line is written to the saved original.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(line, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
 GAMMAS = (4.0, 5.0, 10.0)
 D = 512
 # BASELINE.json configs[0..4]
@@ -190,7 +211,7 @@ def run_reference(args, w):
                 cpu_baseline=dict(value=value, unit="caption-image pairs/s", cores=cores, kind="port", sample=sample,
                                   measured_ms_per_sample_step=t_sample * 1e3, sample_batch=Bs),
                 e2e=dict(value=value, unit="caption-image pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------- NT-Xent (8f-1)
@@ -229,7 +250,7 @@ def run_ntxent(args, w):
     cfgd = dict(workload=args.workload, description=w["desc"], B=B, D=D, temperature=w["temperature"])
     if args.impl == "reference":
         base, t_full = ntxent_cpu(w, args.steps)
-        print(json.dumps(dict(metric="nt_xent_fwd_bwd_rows_per_s", value=base["value"], unit="embedding rows/s",
+        emit(json.dumps(dict(metric="nt_xent_fwd_bwd_rows_per_s", value=base["value"], unit="embedding rows/s",
                               impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                               ms_per_step=t_full * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None,
                               dtype="f32", data="synthetic", config=cfgd, cpu_baseline=base,
@@ -287,7 +308,7 @@ def run_ntxent(args, w):
                 note=("latency-bound: 7 small launches; the exact-fp32 SIMT GEMMs (6*(2B)^2*D flop fwd+bwd = "
                       f"{6.0 * n2 * n2 * D / 1e9:.2f} GFLOP) and the 2B x 2B fp32 logits dominate at large B"))
     base = None if args.no_cpu_baseline else ntxent_cpu(w, 5)[0]
-    print(json.dumps(dict(metric="nt_xent_fwd_bwd_rows_per_s", value=n2 / (ms_step * 1e-3), unit="embedding rows/s",
+    emit(json.dumps(dict(metric="nt_xent_fwd_bwd_rows_per_s", value=n2 / (ms_step * 1e-3), unit="embedding rows/s",
                           n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True,
                           scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
                           config=dict(cfgd, l2="L2 flushed (256 MiB memset) between timed iterations",
@@ -336,7 +357,7 @@ def run_rmtok(args, w):
     cfgd = dict(workload=args.workload, description=w["desc"], B=B, tokens=n, D=D)
     if args.impl == "reference":
         base, t_full = rmtok_cpu(w, args.steps)
-        print(json.dumps(dict(metric="rm_special_token_fwd_bwd_captions_per_s", value=base["value"], unit="captions/s",
+        emit(json.dumps(dict(metric="rm_special_token_fwd_bwd_captions_per_s", value=base["value"], unit="captions/s",
                               impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                               ms_per_step=t_full * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
                               dtype="f32", data="synthetic", config=cfgd, cpu_baseline=base,
@@ -393,7 +414,7 @@ def run_rmtok(args, w):
     roof = dict(bound="hbm", achieved=gbs, peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"], traffic=None,
                 peak_source=peaks["src"], note="two launches (gather, scatter); latency-bound at the pretrain batch")
     base = None if args.no_cpu_baseline else rmtok_cpu(w, 5)[0]
-    print(json.dumps(dict(metric="rm_special_token_fwd_bwd_captions_per_s", value=B / (ms_step * 1e-3), unit="captions/s",
+    emit(json.dumps(dict(metric="rm_special_token_fwd_bwd_captions_per_s", value=B / (ms_step * 1e-3), unit="captions/s",
                           n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True,
                           scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                           config=dict(cfgd, l2="L2 flushed (256 MiB memset) between timed iterations",
@@ -442,7 +463,7 @@ def run_proj(args, w):
     cfgd = dict(workload=args.workload, description=w["desc"], B=B, R=R, K=K, N=N, in_dtype=w["in_dtype"])
     if args.impl == "reference":
         base, t_full = proj_cpu(w, args.steps)
-        print(json.dumps(dict(metric="project_regions_fwd_bwd_images_per_s", value=base["value"], unit="images/s",
+        emit(json.dumps(dict(metric="project_regions_fwd_bwd_images_per_s", value=base["value"], unit="images/s",
                               impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                               ms_per_step=t_full * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
                               dtype="f32", data="synthetic", config=cfgd, cpu_baseline=base,
@@ -521,7 +542,7 @@ def run_proj(args, w):
                 fwd_tflops=flops / (t_f * 1e-3) / 1e12,
                 note="algorithmic bytes: read x and W once, write y (fp32), vhat (fp32), vhat (fp16), norms once")
     base = None if args.no_cpu_baseline else proj_cpu(w, 5)[0]
-    print(json.dumps(dict(metric="project_regions_fwd_bwd_images_per_s", value=B / (ms_step * 1e-3), unit="images/s",
+    emit(json.dumps(dict(metric="project_regions_fwd_bwd_images_per_s", value=B / (ms_step * 1e-3), unit="images/s",
                           n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True,
                           scaling="weak", vs_baseline=None,
                           dtype="bf16 operands / f32 accumulate" if dt == torch.bfloat16 else "tf32 / f32 accumulate",
@@ -546,6 +567,7 @@ def main():
     ap.add_argument("--precision", default=None, choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    capture_stdout()
 
     pkg = importlib.import_module("t2i_clip-gan_b200")
     has_tc = hasattr(pkg._lib.load(), "damsm_words_fwd_tc")      # both arms measure the same workload
@@ -676,7 +698,7 @@ def main():
                     algorithmic_tflops=algorithmic_flops(B, T, R) / (ms_step * 1e-3) / 1e12,
                     losses=loss_vals, wall_ms_per_step=t_wall / args.steps * 1e3,
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu_base)
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if group is not None:
         import torch.distributed as dist
         dist.destroy_process_group()
