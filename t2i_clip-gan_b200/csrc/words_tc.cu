@@ -222,7 +222,6 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int j0 = blockIdx.y * p.img_per_cta;
   const int j1 = min(p.bc, j0 + p.img_per_cta);
   const int T = p.T, R = p.R;
-  const int nsoft = L.act_warps * 32;
   const int nbuf = L.nbuf;
 
   // operand rows past `rs` are read by the MMAs (ignored lanes): make every byte a finite fp16
