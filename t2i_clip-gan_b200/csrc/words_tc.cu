@@ -9,14 +9,16 @@
 //                                                                yields Y_t = sum_r e2 (softmax-over-regions denominator)
 //   regs   N'_t = sum_r e2 S, NN_t = sum_r e2 M'  (warp butterfly + shared memory across warps)
 //          rho_t = (N'/Y) / (max(sqrt(NN)/Y, eps) max(u_t, eps)),  sim = gamma3/gamma2 log sum_t exp(gamma2 rho_t)
-//   bwd    the same recompute, then dS = a A + P (dP - W), dP = gamma1 A (a S - b M), W = sum_t P dP; dS, A and
-//          diag(b) A leave the chip as scaled fp16 tiles that three plain GEMMs (cuBLAS) contract per chunk.
+//   bwd    the same recompute, then dS = a A + P (dP - W), dP = gamma1 A (a S - b M), W = sum_t P dP; dS and A leave
+//          the chip as scaled fp16 rows that two plain GEMMs (cuBLAS: dvhat, dqhat) and hmat_tc.cu (H) contract per chunk.
 //
 // Regions live on the MMA M axis (TMEM lanes): the softmax over words, its backward column term and every
 // per-region quantity are then thread-local, and the accumulators (NT columns per tile) leave TMEM room for a
 // second S buffer, so GEMM1 of the next image overlaps the register work of the current one.
-// Warp roles: 0-15 softmax/epilogue (TMEM lane quadrant = warp%4, tile = (warp/4)%2, word half = warp/8),
-// 16 TMA producer, 17 MMA issuer.  Budgets and the roofline are in DESIGN.md.
+// Warp roles: 0-15 softmax/epilogue (TMEM lane quadrant = warp%4, tile = (warp/4)%2, word half = warp/8); the TMA
+// producer and the MMA issuer are warps 7 and 15 (which own no region row when R+1 <= 224) or two extra warps 16/17.
+// Forward launches pair the CTAs of two captions into a cluster that shares the image stream by TMA multicast.
+// Budgets and the roofline are in DESIGN.md.
 #include <cublas_v2.h>
 #include <stdlib.h>
 #include <type_traits>
