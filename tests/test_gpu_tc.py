@@ -148,3 +148,52 @@ def test_tc_cluster_modes_agree(mode, monkeypatch):
     assert abs(l0.item() - o["loss0"]) <= TOL * max(1, abs(o["loss0"]))
     assert abs(l1.item() - o["loss1"]) <= TOL * max(1, abs(o["loss1"]))
     assert rel(w.grad.cpu().numpy(), o["dwords"]) <= TOL and rel(r.grad.cpu().numpy(), o["dregions"]) <= TOL
+
+
+def test_full_size_properties_c4():
+    """BASELINE configs[3] at full size (B1024 T77 R196, bf16 inputs, tensor-core path) -- far beyond what the oracle can
+    run, so: (i) a sample of caption rows of the score matrix against the exact fp32 CUDA kernel (itself pinned to the
+    oracle) at the full column width; (ii) permuting the batch leaves the losses unchanged and permutes the gradients;
+    (iii) l2norm is scale invariant, so every region's gradient is orthogonal to the region vector."""
+    B, T, R, D = 1024, 77, 196, 512
+    g = torch.Generator().manual_seed(2029)
+    s = torch.randn(B, 1, D, generator=g)
+    # bf16-rounded values held as fp32 tensors, so that the returned gradients are fp32 (bf16 gradients would carry
+    # a 2^-8 rounding of their own, above the bar checked in (ii))
+    words = (0.25 * s + torch.randn(B, T, D, generator=g)).bfloat16().float()
+    regions = (0.25 * s + torch.randn(B, R, D, generator=g)).bfloat16().float()
+    cap_len = torch.randint(T // 3, T + 1, (B,), generator=g)
+    mask = (torch.arange(T).reshape(1, T) < cap_len.reshape(B, 1)).to(torch.int64)
+    labels = torch.arange(B, device="cuda")
+
+    def run(w_h, r_h, m_h):
+        w = w_h.cuda().requires_grad_(True)
+        r = r_h.cuda().requires_grad_(True)
+        l0, l1, _ = pkg.words_loss(r.permute(0, 2, 1), w.permute(0, 2, 1), labels, None, None, B, m_h, 4.0, 5.0, 10.0,
+                                   precision="bf16")
+        (l0 + l1).backward()
+        return l0.item(), l1.item(), w.grad.float(), r.grad.float()
+
+    l0, l1, dw, dr = run(words, regions, mask)
+    assert np.isfinite(l0) and np.isfinite(l1) and 0.0 < l0 < np.log(B) + 1e-3 and 0.0 < l1 < np.log(B) + 1e-3
+    # (i) sampled rows of sim: tensor-core kernel vs exact fp32 kernel, all 1024 columns
+    rows = torch.tensor([0, 1, 17, 511, 512, 1000, 1022, 1023])
+    m8 = mask.cuda().to(torch.uint8)
+    sims = {}
+    for prec in ("fp32", "bf16"):
+        eng = pkg.get_engine(prec)
+        qhat, qhat16, _, qun = eng.l2norm_fwd(words[rows].cuda(), want_bf16=prec == "bf16", pad8=True)
+        vhat, vhat16, _, _ = eng.l2norm_fwd(regions.cuda(), want_bf16=prec == "bf16")
+        col = eng.words_prepare_columns(vhat, vhat16)
+        sims[prec] = eng.words_fwd(qhat, qhat16, vhat, col, qun, m8[rows.cuda()], (4.0, 5.0, 10.0)).float().cpu().numpy()
+    assert np.abs(sims["bf16"] - sims["fp32"]).max() <= TOL * np.abs(sims["fp32"]).max()
+    # (ii) permutation of the batch
+    perm = torch.randperm(B, generator=g)
+    p0, p1, dwp, drp = run(words[perm], regions[perm], mask[perm])
+    assert abs(p0 - l0) <= 1e-4 * max(1.0, abs(l0)) and abs(p1 - l1) <= 1e-4 * max(1.0, abs(l1))
+    pc = perm.cuda()
+    assert float((dwp - dw[pc]).abs().max()) <= TOL * float(dw.abs().max())
+    assert float((drp - dr[pc]).abs().max()) <= TOL * float(dr.abs().max())
+    # (iii) radial component of the region gradient
+    radial = (dr * regions.cuda().float()).sum(-1)
+    assert float(radial.abs().max()) <= 2e-2 * float(dr.abs().max()) * float(regions.float().abs().max()) * D ** 0.5
