@@ -77,10 +77,17 @@ def combine_column_lse(col_max: torch.Tensor, col_sum: torch.Tensor, group):
 _prologue = {}
 
 
-def _prologue_put(y, side):
-    for key in [k for k, (ref, _, _) in _prologue.items() if ref() is None]:
+def _prologue_drop(key, ref):
+    hit = _prologue.get(key)
+    if hit is not None and hit[0] is ref:          # not already replaced by a newer tensor at the same address
         del _prologue[key]
-    _prologue[y.data_ptr()] = (weakref.ref(y), y._version, side)
+
+
+def _prologue_put(y, side):
+    key = y.data_ptr()
+    ref = weakref.ref(y)
+    _prologue[key] = (ref, y._version, side)
+    weakref.finalize(y, _prologue_drop, key, ref)  # the copies (GBs at large batches) die with the projection output
 
 
 def _prologue_get(regions3):
