@@ -90,3 +90,36 @@ def test_tensor_core_shape_query_is_a_host_function():
         assert not pkg.ops.tc_shape_supported(*bad), bad
     with __import__("pytest").raises(ValueError):
         pkg.ops._pick_precision("fp16", 18, 49, 512)
+
+
+def test_no_cpu_fallback_for_the_widened_operators():
+    """CPU tensors never reach a CPU implementation: the C layer (or the wrapper) refuses them."""
+    with pytest.raises((pkg.DamsmError, RuntimeError)):
+        pkg.nt_xent(torch.randn(4, 16), torch.randn(4, 16), 0.5)
+    with pytest.raises((pkg.DamsmError, RuntimeError)):
+        pkg.rm_special_token(torch.ones(3, 6, dtype=torch.int64), torch.randn(3, 6, 8))
+    with pytest.raises((pkg.DamsmError, RuntimeError)):
+        pkg.project_regions(torch.randn(2, 5, 32), torch.randn(16, 32), torch.randn(16))
+    with pytest.raises((pkg.DamsmError, RuntimeError)):
+        pkg.r_precision_scores(torch.randn(2, 8), torch.randn(2, 3, 8))
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No silent fallback when the CUDA library is absent: loading raises with the path and the reason."""
+    monkeypatch.setattr(pkg._lib, "_lib", None)
+    monkeypatch.setattr(pkg._lib, "LIB_PATH", str(tmp_path / "libdamsm_b200.so"))
+    with pytest.raises(pkg.DamsmError, match="no CPU fallback"):
+        pkg._lib.load()
+
+
+def test_reference_import_lines_for_nt_xent_and_masks():
+    """`from nt_xent import NT_Xent`, `from masks import mask_correlated_samples_2` (pretrain_DAMSM.py:34-35)."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); from nt_xent import NT_Xent; "
+            "from masks import mask_correlated_samples, mask_correlated_samples_2; "
+            "m = mask_correlated_samples_2(3); c = NT_Xent(3, 0.5, m, 'cpu'); print(int(m.sum()), c.batch_size)"
+            ) % os.path.join(ROOT, "t2i_clip-gan_b200")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["24", "3"]                 # 6 x 6 minus the diagonal (6) minus the positives (6)
