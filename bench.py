@@ -537,7 +537,10 @@ def run_proj(args, w):
     alg_bytes = B * (R + 1) * K * es + N * K * es + B * R * N * (4 + 4 + 2) + B * R * 8
     gbs = alg_bytes / (t_f * 1e-3) / 1e9
     flops = 2.0 * B * R * K * N
-    roof = dict(bound="hbm", achieved=gbs, peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"], traffic=None,
+    # DRAM bytes of the forward launch from the committed ncu --set full capture (profiles/r1_ncu_tc_summary.md:
+    # 1.253 GB read + 4.066 GB written at B=4096, R=196, bf16 in = 6,626 B per region row; scaled to this shape's rows)
+    traffic = 6626.0 * B * R if (w["in_dtype"] == "bf16" and K == 768 and N == 512) else None
+    roof = dict(bound="hbm", achieved=gbs, peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"], traffic=traffic,
                 peak_source=peaks["src"], kernel="proj_l2norm_tc_kernel (forward)", fwd_ms=t_f,
                 fwd_tflops=flops / (t_f * 1e-3) / 1e12,
                 note="algorithmic bytes: read x and W once, write y (fp32), vhat (fp32), vhat (fp16), norms once")
