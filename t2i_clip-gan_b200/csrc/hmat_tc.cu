@@ -99,12 +99,18 @@ __global__ void __launch_bounds__(HM_THREADS, 1) hmat_tc_kernel(const __grid_con
     // ---- scaled copy of every K-block: sb[r][k] = s_k * sa[r][k]  (same swizzled layout) ----
     const float *sv = p.svec + (int64_t)j * p.kc;
     const int nchunk = p.rs * 8;                                   // 16-byte chunks per stage
+    // the 64 scales of a K block come from global memory: fetch them one block ahead, or their latency sits on the
+    // critical path of every block (all 8 warps wait for them at the named barrier)
+    float sv_next = (threadIdx.x < 64 && threadIdx.x < p.kc) ? sv[threadIdx.x] : 0.f;
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % HM_SA, u = kb % HM_SB;
+      float v = sv_next;
+      if (threadIdx.x < 64) {
+        const int64_t kn = (int64_t)(kb + 1) * 64 + threadIdx.x;
+        sv_next = (kn < p.kc) ? sv[kn] : 0.f;
+      }
       mbar_wait(&b_empty[u], ((kb / HM_SB) & 1) ^ 1);
       if (threadIdx.x < 64) {
-        const int64_t k = (int64_t)kb * 64 + threadIdx.x;
-        float v = (k < p.kc) ? sv[k] : 0.f;
         v = fminf(fmaxf(v, -65504.f), 65504.f);
         ss[u * 64 + threadIdx.x] = __float2half_rn(v);
       }
