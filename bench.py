@@ -2,13 +2,17 @@
 """DAMSM words_loss + sent_loss forward+backward throughput (BASELINE.json metric) on N B200s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c5|...] [--impl ours|reference]
+                    [--scaling strong|weak]
 
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path -- words_loss + sent_loss forward
 and backward (gradients to words, regions, sentence and image codes) -- over one batch of synthetic
 input (SURVEY.md 8d generator).  ``value`` = matched caption-image pairs/s with the inputs already in HBM;
 ``e2e`` = the same through the public drop-in API with pinned host inputs copied to the device and the
 losses read back every step.  For N>1 launch with torchrun (one rank per GPU, NCCL); the global batch is
-fixed and sharded by caption rows (strong scaling).
+fixed and sharded by caption rows (strong scaling, the default); ``--scaling weak`` fixes the LOCAL batch at
+512 caption rows per GPU instead (global 512*N) and is judged on scored pairs/s.
+``--impl reference`` times the reference's own CPU implementation on the host cores and never imports the package
+(no repository .so is mapped by that arm).
 """
 from __future__ import annotations
 
@@ -51,6 +55,9 @@ def emit(line):
 
 GAMMAS = (4.0, 5.0, 10.0)
 D = 512
+# DRAM bytes per scored pair of the word-loss launches (forward 2.8 KB + fused backward 71.6 KB written/read once;
+# the gradient GEMMs and the H kernel re-read the scratch: + 3 x 31.4 KB), profiles/r1_ncu_tc_summary.md
+TRAFFIC_BYTES_PER_PAIR = 2.8e3 + 71.6e3 + 3 * 31.4e3
 # BASELINE.json configs[0..4]
 WORKLOADS = {
     "c1": dict(B=48, T=18, R=49, cls=True, precision="fp32", seed=2026, desc="CUB bird DAMSM shape"),
@@ -87,8 +94,13 @@ def make_inputs(w, dtype):
     regions = (0.25 * s + torch.randn(B, R, D, generator=g)).to(dtype)
     sent = (0.25 * s[:, 0] + torch.randn(B, D, generator=g)).to(dtype)
     img = (0.25 * s[:, 0] + torch.randn(B, D, generator=g)).to(dtype)
-    lo = max(2, T // 3)
-    cap_len = torch.randint(lo, T + 1, (B,), generator=g)
+    if w.get("lens") == "clip":
+        # CLIP-tokenised COCO/CUB captions: mostly 8-20 tokens, a thin tail up to the context length
+        # (log-normal, median 12, sigma 0.35, clipped to [3, T]) -- the realistic case next to SURVEY 8d's uniform one
+        cap_len = torch.exp(torch.randn(B, generator=g) * 0.35 + float(np.log(12.0))).round().clamp(3, T).to(torch.int64)
+    else:
+        lo = max(2, T // 3)
+        cap_len = torch.randint(lo, T + 1, (B,), generator=g)
     mask = (torch.arange(T).reshape(1, T) < cap_len.reshape(B, 1)).to(torch.int64)
     cls = torch.randint(0, 200, (B,), generator=g).numpy() if w["cls"] else None
     return dict(words=words, regions=regions, sent=sent, img=img, mask=mask, cap_len=cap_len, class_ids=cls)
@@ -179,11 +191,34 @@ def barrier(group):
     torch.cuda.synchronize()
 
 
-# --------------------------------------------------------------------------------------------- reference arm
-def run_reference(args, w):
-    """The reference's own CPU procedure (oracle/ref_port.py: the reference is pure Python and does not
-    travel to the GPU box) on the host cores, on a bounded sample of the workload."""
+# --------------------------------------------------------------------------------------------- shared by both arms
+def workload_config(args, w, world=1):
+    """The ``config`` object of the JSON line: identical keys (and, for the same command line, values) in both arms."""
+    B = w["B"]
+    return dict(workload=args.workload, description=w["desc"], global_batch=B, local_batch=B // world,
+                T=w["T"], R=w["R"], D=D, class_mask=bool(w["cls"]), gammas=list(GAMMAS), precision=w["precision"],
+                parallelism=f"caption-row shards x{world}" if world > 1 else "single GPU",
+                scaling=args.scaling, caption_lengths=w.get("lens", "uniform"),
+                step="words_loss + sent_loss forward + backward, grads to all 4 inputs")
+
+
+def cpu_step():
+    """(callable(x, gammas), kind): the reference's own losses.py when it is importable here (from /root/reference or
+    from the byte code oracle/build_ref.py put under oracle/_ref) -> kind "reference"; else the procedure port."""
+    from oracle import ref_shim
+    if ref_shim.available():
+        try:
+            ref_shim.load()
+            return ref_shim.ref_step, "reference"
+        except Exception as e:                                   # e.g. a dependency of losses.py missing on this host
+            print(f"bench: reference not importable ({e!r}); timing the port", file=sys.stderr)
     from oracle import ref_port
+    return ref_port.step, "port"
+
+
+def time_cpu_reference(w, steps, warmup=1, budget_s=25.0):
+    """words_loss + sent_loss fwd+bwd of the reference on the host cores, on a bounded sample of the workload."""
+    fn, kind = cpu_step()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     B = w["B"]
@@ -192,26 +227,39 @@ def run_reference(args, w):
     x = make_inputs(ws, torch.float32)
     xin = {k: (v.numpy() if torch.is_tensor(v) else v) for k, v in x.items()}
     xin["labels"] = np.arange(Bs)
-    for _ in range(max(1, min(args.warmup, 1))):
-        ref_port.step(xin, GAMMAS)
+    for _ in range(max(1, warmup)):
+        fn(xin, GAMMAS)
     ts = []
-    for _ in range(args.steps):
+    t_end = time.perf_counter() + budget_s
+    while len(ts) < steps and (time.perf_counter() < t_end or len(ts) < 2):
         t0 = time.perf_counter()
-        ref_port.step(xin, GAMMAS)
+        fn(xin, GAMMAS)
         ts.append(time.perf_counter() - t0)
     t_sample = float(np.median(ts))
     t_full = t_sample * (B / Bs) ** 2   # time grows with the number of scored pairs
-    value = B / t_full
     sample = (f"{Bs}x{Bs} pairs of the workload (T={w['T']}, R={w['R']}, fp32), words_loss+sent_loss fwd+bwd, "
-              f"median of {args.steps}; " + ("full size" if Bs == B else f"extrapolated to B={B} with time ~ B^2"))
+              f"median of {len(ts)}; " + ("full size" if Bs == B else f"extrapolated to B={B} with time ~ B^2"))
+    return dict(value=B / t_full, unit="caption-image pairs/s", cores=cores, kind=kind, sample=sample,
+                measured_ms_per_sample_step=t_sample * 1e3, sample_batch=Bs), t_full
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, w):
+    """The reference's own CPU implementation of the path on the host cores (oracle/_ref byte code of the unmodified
+    losses.py when present, else oracle/ref_port.py), on a bounded sample of the workload.  Never touches the GPU."""
+    base, t_full = time_cpu_reference(w, args.steps, args.warmup)
+    value = base["value"]
     line = dict(metric="damsm_fwd_bwd_matched_pairs_per_s", value=value, unit="caption-image pairs/s", impl="reference",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=t_full * 1e3,
-                higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=args.workload, B=B, T=w["T"], R=w["R"], D=D, description=w["desc"]),
-                cpu_baseline=dict(value=value, unit="caption-image pairs/s", cores=cores, kind="port", sample=sample,
-                                  measured_ms_per_sample_step=t_sample * 1e3, sample_batch=Bs),
+                higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32", data="synthetic",
+                config=workload_config(args, w, int(os.environ.get("WORLD_SIZE", "1"))),
+                cpu_baseline=base,
                 e2e=dict(value=value, unit="caption-image pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(json.dumps(line))
+    if os.environ.get("DAMSM_BENCH_LIST_MAPS"):       # tests: prove that this arm mapped no repository .so
+        with open("/proc/self/maps") as f:
+            libs = sorted({ln.split()[-1] for ln in f if ROOT in ln and ".so" in ln})
+        print("mapped-libraries:", libs, file=sys.stderr)
 
 
 # --------------------------------------------------------------------------------------------- NT-Xent (8f-1)
@@ -569,16 +617,23 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=None, choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: fixed global batch sharded by rows; weak: 512 caption rows per GPU (global 512*N)")
+    ap.add_argument("--lens", default=None, choices=["uniform", "clip"],
+                    help="caption-length distribution: uniform U[T/3,T] (SURVEY 8d, default) or a CLIP/COCO-like histogram")
     args = ap.parse_args()
     capture_stdout()
 
-    pkg = importlib.import_module("t2i_clip-gan_b200")
-    has_tc = hasattr(pkg._lib.load(), "damsm_words_fwd_tc")      # both arms measure the same workload
     if args.workload is None:
-        args.workload = "c5" if has_tc else "c2"
+        args.workload = "c5"        # the configuration the metric is quoted on (BASELINE.json configs[4])
     w = dict(WORKLOADS[args.workload])
     if args.precision:
         w["precision"] = args.precision
+    if args.lens:
+        w["lens"] = args.lens
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.scaling == "weak" and "T" in w:
+        w["B"] = 512 * max(world_env, args.gpus if world_env == 1 else world_env)
     if args.steps is None:
         args.steps = 5 if w["B"] >= 1024 else 20
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -587,11 +642,12 @@ def main():
             (run_ntxent if w.get("ntxent") else run_rmtok if w.get("rmtok") else run_proj)(args, w)
         return
 
-    if args.impl == "reference":
+    if args.impl == "reference":    # before the package is imported: this arm maps no repository .so
         if int(os.environ.get("RANK", "0")) == 0:
             run_reference(args, w)
         return
 
+    pkg = importlib.import_module("t2i_clip-gan_b200")
     world, rank, local, group = dist_setup(args.gpus)
     B, T, R = w["B"], w["T"], w["R"]
     assert B % world == 0, "global batch must divide by the number of GPUs"
@@ -681,30 +737,62 @@ def main():
     e2e = dict(value=B / e2e_s, unit="caption-image pairs/s", ms_per_step=e2e_s * 1e3,
                h2d_bytes_per_step=int(h2d * world), d2h_bytes_per_step=int(d2h * world))
 
-    # ---- roofline of the dominant kernels, timed alone with CUDA events on the launching stream ------------------
-    roof = measure_roofline(pkg, w, dev, bl, B, rank, group, prec)
+    # ---- roofline: algorithmic flops of the step / the timed step; the fwd / bwd launches re-timed alone explain it ---
+    roof = measure_roofline(pkg, w, dev, bl, B, rank, group, prec, ms_step)
+
+    # ---- N > 1: sharded vs unsharded losses and gradients on a small side case (kept in the SCALE record) ---------
+    shard_parity = measure_shard_parity(pkg, world, rank, group, prec) if world > 1 else None
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base = measure_cpu_baseline(w)
+        cpu_base = time_cpu_reference(w, 5)[0]
 
     if rank == 0:
+        scored = B * B / (ms_step * 1e-3)
         line = dict(metric="damsm_fwd_bwd_matched_pairs_per_s", value=value, unit="caption-image pairs/s",
                     n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
-                    higher_is_better=True, scaling="strong", vs_baseline=None,
+                    higher_is_better=True, scaling=args.scaling, vs_baseline=None,
                     dtype="bf16 operands / f32 accumulate" if prec == "bf16" else "f32", data="synthetic",
-                    config=dict(workload=args.workload, description=w["desc"], global_batch=B, local_batch=bl,
-                                T=T, R=R, D=D, class_mask=bool(w["cls"]), gammas=list(GAMMAS), precision=prec,
-                                parallelism=f"caption-row shards x{world}" if world > 1 else "single GPU",
-                                l2=l2_note, step="words_loss + sent_loss forward + backward, grads to all 4 inputs"),
-                    scored_pairs_per_s=B * B / (ms_step * 1e-3),
+                    config=dict(workload_config(args, w, world), l2=l2_note),
+                    scored_pairs_per_s=scored, scored_pairs_per_s_per_gpu=scored / world,
                     algorithmic_tflops=algorithmic_flops(B, T, R) / (ms_step * 1e-3) / 1e12,
                     losses=loss_vals, wall_ms_per_step=t_wall / args.steps * 1e3,
-                    clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu_base)
+                    clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu_base,
+                    shard_parity=shard_parity)
         emit(json.dumps(line))
     if group is not None:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def measure_shard_parity(pkg, world, rank, group, prec):
+    """Row-sharded (this run's process group) vs unsharded (every rank recomputes the full batch alone) losses and
+    gradients of words_loss + sent_loss on a small seeded case; max over ranks.  tools/dist_check.py is the long form."""
+    import torch.distributed as dist
+    B, T, R = 16 * world, (77 if prec == "bf16" else 18), (196 if prec == "bf16" else 49)
+    x = make_inputs(dict(B=B, T=T, R=R, seed=777, cls=True), torch.float32)
+    bl = B // world
+    lo, hi = rank * bl, (rank + 1) * bl
+    labels = torch.arange(B, device="cuda")
+
+    def run(sl, grp):
+        t = {k: x[k][sl].cuda().requires_grad_(True) for k in ("words", "regions", "sent", "img")}
+        n = t["words"].shape[0]
+        cls = x["class_ids"][sl]
+        w0, w1, _ = pkg.words_loss(t["regions"].permute(0, 2, 1), t["words"].permute(0, 2, 1), labels, None, cls, n,
+                                   x["mask"][sl], *GAMMAS, precision=prec, group=grp)
+        s0, s1 = pkg.sent_loss(t["img"], t["sent"], labels, cls, n, gamma3=GAMMAS[2], group=grp)
+        (w0 + w1 + s0 + s1).backward()
+        return torch.stack([w0, w1, s0, s1]).detach(), [t[k].grad for k in ("words", "regions", "sent", "img")]
+
+    ls, gs = run(slice(lo, hi), group)
+    lf, gf = run(slice(0, B), None)
+    el = float(((ls - lf).abs() / lf.abs().clamp_min(1.0)).max())
+    eg = max(float((a - b[lo:hi]).abs().max() / b.abs().max()) for a, b in zip(gs, gf))
+    t = torch.tensor([el, eg], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return dict(case=f"B={B} T={T} R={R} class mask on, {prec}", loss_rel_err=float(t[0]), grad_rel_err=float(t[1]),
+                tolerance=2e-3 if prec == "bf16" else 2e-5)
 
 
 def load_peaks():
@@ -715,9 +803,10 @@ def load_peaks():
     return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, src="fallback")
 
 
-def measure_roofline(pkg, w, dev, bl, B, rank, group, prec):
-    """Time the dominant kernel (the fused word/region pair kernels, forward + backward launches) alone.
-    achieved = algorithmic flops of those launches / their measured duration; peak = measured bf16 dense."""
+def measure_roofline(pkg, w, dev, bl, B, rank, group, prec, ms_step):
+    """achieved = algorithmic flops of the step (12 B_rows B T R D + 6 B_rows B D) / the CUDA-event time of
+    the timed step (max over ranks), per GPU; peak = measured bf16 dense (burst; the sustained figure beside it).
+    The forward launch and the backward launches are re-timed alone afterwards to show where the step goes."""
     eng = pkg.get_engine(prec)
     T, R = w["T"], w["R"]
     peaks = load_peaks()
@@ -748,61 +837,29 @@ def measure_roofline(pkg, w, dev, bl, B, rank, group, prec):
             return e0.elapsed_time(e1) / reps
 
         t_f = timed(lambda: eng.words_fwd(qhat, qhat16, vhat, col, qunorm, mask_u8, GAMMAS))
-        bwd = lambda: eng.words_bwd(qhat, qhat16, vhat, col, qunorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
-                                    rank * bl, B, GAMMAS)
-        t_b = timed(bwd)
-        t_b_fused = None
-        if prec == "bf16":      # the fused tcgen05 recompute kernel alone (library switch skips the gradient GEMMs)
-            os.environ["DAMSM_BWD_FUSED_ONLY"] = "1"
-            try:
-                t_b_fused = timed(bwd)
-            finally:
-                del os.environ["DAMSM_BWD_FUSED_ONLY"]
+        t_b = timed(lambda: eng.words_bwd(qhat, qhat16, vhat, col, qunorm, mask_u8, sim, row_lse, col_lse, labels,
+                                          gscale, rank * bl, B, GAMMAS))
     f_fwd = 4.0 * bl * B * T * R * D
     f_bwd = 8.0 * bl * B * T * R * D
-    ach = (f_fwd + f_bwd) / ((t_f + t_b) * 1e-3) / 1e12
-    # DRAM traffic of the two fused tcgen05 kernels per scored pair, from the committed ncu --set full capture
-    # (profiles/r1_ncu_tc_summary.md: forward 2.8 KB, backward 71.6 KB -- the fp16 dS/A scratch rows); fp32 path: none captured
-    traffic = (2.8e3 + 71.6e3) * bl * B if prec == "bf16" else None
+    f_step = 12.0 * bl * B * T * R * D + 6.0 * bl * B * D
+    ach = f_step / (ms_step * 1e-3) / 1e12
     sustained = peaks.get("bf16_sustained")
+    # DRAM traffic of the word-loss launches per scored pair from the committed ncu --set full captures
+    # (profiles/r2_ncu_summary.md); the capture is at B=256, the per-pair figure is scaled by this step's pairs
+    traffic = TRAFFIC_BYTES_PER_PAIR * bl * B if (prec == "bf16" and TRAFFIC_BYTES_PER_PAIR) else None
     return dict(bound="tensor", achieved=ach, peak=peaks["bf16"], unit="TFLOP/s", frac=ach / peaks["bf16"],
                 peak_sustained=sustained, frac_of_sustained=(ach / sustained if sustained else None),
-                traffic=traffic, traffic_note="bytes per step of the fused fwd+bwd kernels = ncu dram bytes per pair x pairs", peak_source=peaks["src"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
-                kernel=("word-loss operator: words_tc_kernel<FWD> (1 launch) + backward (words_tc_kernel<BWD> per chunk, "
-                        "hmat_tc_kernel, 2 cuBLAS GEMMs per chunk); algorithmic flops (4+8)*B_rows*B*T*R*D"
-                        if prec == "bf16" else
-                        "words_pair_f32_kernel fwd + bwd launches; algorithmic flops (4+8)*B_rows*B*T*R*D"),
-                fwd_ms=t_f, bwd_ms=t_b, bwd_fused_kernel_ms=t_b_fused,
-                bwd_gemms_ms=(t_b - t_b_fused) if t_b_fused is not None else None,
+                traffic=traffic,
+                traffic_note=("from capture: ncu dram__bytes_read+write per scored pair of the word-loss launches at B=256 "
+                              "x this step's pairs (not measured in this run)"),
+                peak_source=peaks["src"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
+                kernel=("whole step (words_loss + sent_loss fwd+bwd); dominant launches: words_tc_kernel<FWD>, "
+                        "words_tc_kernel<BWD> + gradient GEMMs + hmat_tc_kernel per chunk"
+                        if prec == "bf16" else "whole step; dominant launches: words_pair_f32_kernel fwd + bwd"),
+                fwd_ms=t_f, bwd_ms=t_b,
                 fwd_tflops=f_fwd / (t_f * 1e-3) / 1e12, bwd_tflops=f_bwd / (t_b * 1e-3) / 1e12,
                 note=("exact fp32 SIMT path: the tensor roofline is quoted for comparison only; this configuration is "
                       "latency-bound (SURVEY 8d)") if prec == "fp32" else "bf16 tcgen05 path")
-
-
-def measure_cpu_baseline(w):
-    """oracle/ref_port.py (procedure port of the reference) on this box's host cores, bounded sample."""
-    from oracle import ref_port
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    B = w["B"]
-    Bs = B if B <= 64 else 32
-    ws = dict(w, B=Bs)
-    x = make_inputs(ws, torch.float32)
-    xin = {k: (v.numpy() if torch.is_tensor(v) else v) for k, v in x.items()}
-    xin["labels"] = np.arange(Bs)
-    ref_port.step(xin, GAMMAS)
-    ts = []
-    t_budget = time.perf_counter() + 20.0
-    while len(ts) < 5 and (time.perf_counter() < t_budget or len(ts) < 2):
-        t0 = time.perf_counter()
-        ref_port.step(xin, GAMMAS)
-        ts.append(time.perf_counter() - t0)
-    t_sample = float(np.median(ts))
-    t_full = t_sample * (B / Bs) ** 2
-    return dict(value=B / t_full, unit="caption-image pairs/s", cores=cores, kind="port",
-                sample=(f"{Bs}x{Bs} pairs (T={w['T']}, R={w['R']}, fp32) fwd+bwd, median of {len(ts)}; "
-                        + ("full size" if Bs == B else f"extrapolated to B={B} with time ~ B^2")),
-                measured_ms_per_sample_step=t_sample * 1e3, sample_batch=Bs)
 
 
 if __name__ == "__main__":

@@ -122,6 +122,11 @@ DAMSM_API int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void 
  *   hmat (bc,R,R) += A^T diag(b) A [ACCUMULATED]                   kq (br,T)                       [ACCUMULATED]
  * qhat16 must be padded: q_rows == T rounded up to a multiple of 8. */
 DAMSM_API int64_t damsm_words_bwd_tc_row_bytes(int64_t bc, int64_t t, int64_t r);
+/* Bytes at the head of `workspace` that hold the device scalars of one call (the upstream gradients g0, g1 normalised
+ * by max(|g0|,|g1|), that maximum, and the epilogue scales): workspace_bytes >= fixed + rows * row_bytes.  The fp16
+ * range of the scratch rows therefore does not depend on the loss weight (`(w_loss0 + w_loss1) * LAMBDA`,
+ * losses.py:355; an AMP loss scale). */
+DAMSM_API int64_t damsm_words_bwd_tc_fixed_bytes(void);
 DAMSM_API int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
                                    const float *unorm, const uint8_t *mask, const float *sim, const float *stats,
                                    const float *row_lse, const float *col_lse, const int64_t *labels,

@@ -1,4 +1,5 @@
-"""Import the UNMODIFIED reference (``/root/reference``) in the build container.  TEST INFRASTRUCTURE ONLY.
+"""Import the UNMODIFIED reference (``/root/reference``, or its byte-compiled hot-path modules under
+``oracle/_ref`` built by ``oracle/build_ref.py`` where the sources do not exist).  TEST INFRASTRUCTURE ONLY.
 
 Used by ``oracle/make_golden.py`` (to record golden vectors) and by
 ``tests/test_oracle_vs_reference.py`` (live comparison, skipped where
@@ -20,11 +21,27 @@ import sys
 import types
 import warnings
 
-REF_ROOT = "/root/reference/DMGAN+CLIP/code"
+SRC_ROOT = "/root/reference/DMGAN+CLIP/code"
+BUILT_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _built_ok() -> bool:
+    tag = os.path.join(BUILT_ROOT, "PYTHON_TAG")
+    return (os.path.isfile(os.path.join(BUILT_ROOT, "miscc", "losses.pyc")) and os.path.isfile(tag)
+            and open(tag).read().strip() == sys.implementation.cache_tag)
+
+
+def sources_available() -> bool:
+    """The reference SOURCES are present (build container): needed by the ast-extracting helpers."""
+    return os.path.isfile(os.path.join(SRC_ROOT, "miscc", "losses.py"))
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "miscc", "losses.py"))
+    """The reference's hot-path modules can be imported (from source, or from oracle/_ref byte code)."""
+    return sources_available() or _built_ok()
+
+
+REF_ROOT = SRC_ROOT if (sources_available() or not _built_ok()) else BUILT_ROOT
 
 
 class _EasyDict(dict):
@@ -76,11 +93,12 @@ def load():
 
 
 @contextlib.contextmanager
-def cpu_patches():
-    """Neutralise the two hard-coded CUDA-isms (losses.py:127, :145) on a CPU-only host."""
+def cpu_patches(force_cpu: bool = False):
+    """Neutralise the two hard-coded CUDA-isms (losses.py:127, :145) on a CPU-only host, or -- ``force_cpu`` -- on a
+    GPU box when the reference is to be timed on the host cores (bench.py's CPU baseline)."""
     import torch
     losses, ga, cfg = load()
-    if torch.cuda.is_available():
+    if torch.cuda.is_available() and not force_cpu:
         cfg.CUDA = True
         yield
         return
@@ -155,7 +173,8 @@ def ref_nt_xent(z_i, z_j, temperature):
     import torch
     mods = []
     for name in ("nt_xent", "masks"):
-        spec = importlib.util.spec_from_file_location("_ref_" + name, os.path.join(REF_ROOT, name + ".py"))
+        path = os.path.join(REF_ROOT, name + ".py")
+        spec = importlib.util.spec_from_file_location("_ref_" + name, path if os.path.isfile(path) else path + "c")
         m = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(m)
         mods.append(m)
@@ -176,10 +195,36 @@ def ref_rm_special_token(mask, words_emb):
     import ast
     import numpy as np
     import torch
-    path = os.path.join(REF_ROOT, "pretrain_DAMSM.py")
+    path = os.path.join(SRC_ROOT, "pretrain_DAMSM.py")
     src = open(path).read()
     fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "rm_special_token")
     ns = {"torch": torch}
     exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
     emb, m = ns["rm_special_token"](torch.as_tensor(np.asarray(mask)), torch.as_tensor(np.asarray(words_emb)))
     return emb.numpy().copy(), m.numpy().copy()
+
+
+def ref_step(x, gammas):
+    """One pass of the reference's own hot path on the HOST cores: words_loss + sent_loss forward + backward
+    (losses.py:219-272, :51-91) on torch-CPU tensors, gradients to all four inputs.  ``x``: dict of numpy arrays
+    (words (B,T,D), regions (B,R,D), sent, img (B,D), mask (B,T), cap_len, class_ids|None, labels).  What
+    ``bench.py --impl reference`` / ``cpu_baseline`` time when the reference is importable (kind "reference")."""
+    import numpy as np
+    import torch
+    losses, _, cfg = load()
+    w = torch.tensor(np.asarray(x["words"]), dtype=torch.float32, requires_grad=True)
+    r = torch.tensor(np.asarray(x["regions"]), dtype=torch.float32, requires_grad=True)
+    a = torch.tensor(np.asarray(x["img"]), dtype=torch.float32, requires_grad=True)
+    t = torch.tensor(np.asarray(x["sent"]), dtype=torch.float32, requires_grad=True)
+    B = w.shape[0]
+    m = torch.tensor(np.asarray(x["mask"]), dtype=torch.int64)
+    lab = torch.tensor(np.asarray(x["labels"]), dtype=torch.int64)
+    cl = torch.tensor(np.asarray(x["cap_len"]), dtype=torch.int64)
+    cls = None if x.get("class_ids") is None else np.asarray(x["class_ids"])
+    cfg.TRAIN.SMOOTH.GAMMA3 = float(gammas[2])
+    with cpu_patches(force_cpu=True):
+        w0, w1, _ = losses.words_loss(r.permute(0, 2, 1), w.permute(0, 2, 1), lab, cl, cls, B, m,
+                                      float(gammas[0]), float(gammas[1]), float(gammas[2]))
+        s0, s1 = losses.sent_loss(a, t, lab, cls, B)
+        (w0 + w1 + s0 + s1).backward()
+    return [float(v.detach()) for v in (w0, w1, s0, s1)]

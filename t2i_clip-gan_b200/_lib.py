@@ -33,6 +33,7 @@ SIGNATURES = {
     "damsm_words_tc_smem_bytes": [_l, _l, _l],
     "damsm_words_fwd_tc": [_p, _l, _p, _p, _p, _p, _l, _l, _l, _l, _l, _f, _f, _f, _p, _p, _p],
     "damsm_words_bwd_tc_row_bytes": [_l, _l, _l],
+    "damsm_words_bwd_tc_fixed_bytes": [],
     "damsm_words_bwd_tc": [_p, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _l, _l, _l, _f, _f, _f,
                              _p, _l, _p, _p, _p, _p, _p],
     "damsm_ce_stats_f32": [_p, _p, _p, _l, _l, _l, _p, _p, _p, _p],
@@ -52,7 +53,7 @@ SIGNATURES = {
 }
 _RESTYPE = {"damsm_last_error": C.c_char_p, "damsm_words_f32_smem_bytes": C.c_int64,
             "damsm_words_tc_gx_cols": C.c_int64, "damsm_words_tc_smem_bytes": C.c_int64,
-            "damsm_words_bwd_tc_row_bytes": C.c_int64}
+            "damsm_words_bwd_tc_row_bytes": C.c_int64, "damsm_words_bwd_tc_fixed_bytes": C.c_int64}
 
 # kernels launched per successful call of each entry point (bench.py reports the total as gpu_launches)
 LAUNCHES = {

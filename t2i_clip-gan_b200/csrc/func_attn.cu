@@ -58,7 +58,9 @@ __global__ void __launch_bounds__(WF_THREADS) func_attention_fwd_kernel(FaParams
       for (int e = tid; e < (T + R) * (FA_KC / 4); e += WF_THREADS) {
         const int row = e / (FA_KC / 4), c4 = e % (FA_KC / 4);
         const float *src = (row < T) ? (q + (int64_t)row * D) : (v + (int64_t)(row - T) * D);
-        *reinterpret_cast<float4 *>(stage + row * LDK + 4 * c4) = *reinterpret_cast<const float4 *>(src + k0 + 4 * c4);
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);       // zero-filled tail when D % FA_KC != 0
+        if (k0 + 4 * c4 < D) val = *reinterpret_cast<const float4 *>(src + k0 + 4 * c4);
+        *reinterpret_cast<float4 *>(stage + row * LDK + 4 * c4) = val;
       }
       __syncthreads();
       if (SMALL) tile_nt<2, 2>(stage, LDK, stage + T * LDK, LDK, S, rp, T, R, FA_KC, tid);
@@ -145,8 +147,10 @@ __global__ void __launch_bounds__(WF_THREADS) func_attention_bwd_kernel(FaParams
       __syncthreads();
       for (int e = tid; e < (T + R) * FA_KC; e += WF_THREADS) {
         const int row = e / FA_KC, kk = e - row * FA_KC;
-        stage[row * LDK + kk] = (row < T) ? dwc[(int64_t)row * D + k0 + kk]
-                                          : c[(int64_t)(row - T) * p.csr + (int64_t)(k0 + kk) * p.csd];
+        float val = 0.f;                                    // zero-filled tail when D % FA_KC != 0
+        if (k0 + kk < D)
+          val = (row < T) ? dwc[(int64_t)row * D + k0 + kk] : c[(int64_t)(row - T) * p.csr + (int64_t)(k0 + kk) * p.csd];
+        stage[row * LDK + kk] = val;
       }
       __syncthreads();
       if (SMALL) tile_nt<2, 2>(stage, LDK, stage + T * LDK, LDK, X, rp, T, R, FA_KC, tid);

@@ -21,7 +21,7 @@ struct HmatParams {
   int R, rs, tiles, n16;          // rows, rows per stage (ceil16 R), M tiles, N of the MMA
   int64_t kc;                     // K extent of this chunk
   const float *svec;              // (bc, kc) fp32: s_k already multiplied by the power-of-two fp16 scale
-  float alpha;                    // undoes that scale
+  const float *alpha;             // device scalar that undoes that scale (and carries the upstream-gradient magnitude)
   float *hmat;                    // (bc, R, R) fp32, accumulated
 };
 
@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(HM_THREADS, 1) hmat_tc_kernel(const __grid_con
     tc_fence_after();
     const int tile = warp >> 2;
     const int r = tile * 128 + (warp & 3) * 32 + lane;
+    const float alpha = *p.alpha;
     if (tile < p.tiles) {
       const uint32_t t0 = tmem_base + (((uint32_t)(warp & 3) * 32) << 16) + tile * p.n16;
       float *hrow = p.hmat + ((int64_t)j * p.R + (r < p.R ? r : 0)) * p.R;
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(HM_THREADS, 1) hmat_tc_kernel(const __grid_con
         if (r < p.R) {
 #pragma unroll
           for (int k = 0; k < 16; ++k)
-            if (c0 + k < p.R) hrow[c0 + k] += p.alpha * x[k];
+            if (c0 + k < p.R) hrow[c0 + k] += alpha * x[k];
         }
       }
     }
@@ -161,7 +162,7 @@ int make_map_f16(CUtensorMap *m, const void *base, uint64_t n0, uint64_t n1, uin
                  uint64_t pitch2_elems, uint32_t box1);   // words_tc.cu
 
 // A: (bc*R, kc) fp16 row-major scratch; svec (bc, kc); hmat (bc, R, R) accumulated
-int launch_hmat_tc(const void *x_a, const float *svec, int64_t bc, int64_t r, int64_t kc, float alpha, float *hmat,
+int launch_hmat_tc(const void *x_a, const float *svec, int64_t bc, int64_t r, int64_t kc, const float *alpha, float *hmat,
                    cudaStream_t st) {
   DAMSM_REQUIRE(r >= 1 && r <= 255 && kc % 8 == 0, "hmat_tc: bad shape R=%lld kc=%lld", (long long)r, (long long)kc);
   HmatParams p{};

@@ -118,7 +118,9 @@ __global__ void __launch_bounds__(WF_THREADS) words_pair_f32_kernel(WordsParams 
       for (int e = tid; e < (T + R) * (WF_KC / 4); e += WF_THREADS) {
         const int row = e / (WF_KC / 4), c4 = e % (WF_KC / 4);
         const float *src = (row < T) ? (q + (int64_t)row * D) : (v + (int64_t)(row - T) * D);
-        const float4 val = *reinterpret_cast<const float4 *>(src + k0 + 4 * c4);
+        // the last k-chunk of a D that is not a multiple of WF_KC is zero-filled (D % 4 == 0 keeps float4 loads whole)
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + 4 * c4 < D) val = *reinterpret_cast<const float4 *>(src + k0 + 4 * c4);
         *reinterpret_cast<float4 *>(stage + row * LDK + 4 * c4) = val;
       }
       __syncthreads();

@@ -89,7 +89,8 @@ struct TcParams {
   int i0;              // first caption row of this chunk (blockIdx.x is relative to it)
   int tp;              // T padded to a multiple of 8: words per caption in the scratch matrices
   int64_t kc;          // scratch row length = chunk_rows * tp
-  const float *row_lse, *col_lse, *gscale;
+  const float *row_lse, *col_lse;
+  const float *gscale;                // device scalars: [0],[1] = g0,g1 / max(|g0|,|g1|); [2] = that maximum
   const int64_t *labels;
   int64_t row_offset, b_total;
   float *kq;
@@ -403,13 +404,16 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int widx = (warp & 7) * 32 + lane;                        // row slot in zbuf / wbuf
     constexpr int CPL = (NT + 31) / 32;                             // words per lane in the one-warp sections
     // backward, warp 0: per-row constants of dL/dsim (both cross-entropies, losses.py:265-269)
-    float bw_rl = 0.f, bw_g0 = 0.f, bw_g1 = 0.f, bw_ib = 0.f;
+    float bw_rl = 0.f, bw_g0 = 0.f, bw_g1 = 0.f, bw_ib = 0.f, bw_gm = 0.f;
     int64_t bw_gi = 0, bw_li = 0;
     if (BWD && warp == 0) {
       bw_gi = p.row_offset + i;
       bw_li = p.labels ? p.labels[bw_gi] : bw_gi;
       bw_rl = p.row_lse[i];
-      bw_g0 = p.gscale[0]; bw_g1 = p.gscale[1];
+      // the upstream gradients enter normalised by their larger magnitude, which is folded back into the GEMM / H
+      // epilogue scale and into kq: the fp16 range of the scratch rows then does not depend on the loss weight
+      // (LAMBDA = 50 in clip_coco_DMGAN.yml, an AMP loss scale of 2^16, ...)
+      bw_g0 = p.gscale[0]; bw_g1 = p.gscale[1]; bw_gm = p.gscale[2];
       bw_ib = 1.f / (float)p.b_total;
     }
     // ---- serial tail of the forward, one warp: per-word cosine (losses.py:197-198), gamma2 log-sum-exp (:199-203),
@@ -588,7 +592,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               vcb[t] = make_float4(p.g1 * a * iy, p.g1 * bq * iy * iy, a * iy * p.scale_ds, 0.f);
               p.svec[(int64_t)j * p.kc + (int64_t)blockIdx.x * p.tp + t] = bq * p.scale_ba;
               viyb[t] = iy;
-              atomicAdd(p.kq + (int64_t)i * T + t, beta * rho);
+              atomicAdd(p.kq + (int64_t)i * T + t, beta * rho * bw_gm);
             } else if (t < p.tp) {
               p.svec[(int64_t)j * p.kc + (int64_t)blockIdx.x * p.tp + t] = 0.f;
             }
@@ -819,10 +823,24 @@ static int tc_prepare(TcLaunch *tl, const char *who, const void *qhat16, int64_t
 
 template <bool BWD>
 static int tc_launch(const TcLaunch &tl, TcParams &p, int64_t rows, cudaStream_t st) {
-  // split the image range so that the grid covers the SMs a few times over
-  int splits = (int)((4LL * tl.sms + rows - 1) / rows);
-  if (splits < 1) splits = 1;
-  if (splits > p.bc) splits = p.bc;
+  // Split the image range so that the grid is as close as possible to a whole number of waves of the SM count
+  // (1 CTA per SM): every CTA of a launch does the same work, so a partial last wave idles SMs for a full CTA time
+  // (654 CTAs on 148 SMs = 4.42 waves cost 12 % of every backward chunk in round 1).
+  int splits = 1;
+  {
+    double best = -1.0;
+    const int max_splits = (int)((p.bc < 16) ? p.bc : 16);
+    for (int sp = 1; sp <= max_splits; ++sp) {
+      const int ipc = (p.bc + sp - 1) / sp;
+      const int real = (p.bc + ipc - 1) / ipc;
+      const int64_t ctas = rows * real;
+      const int64_t waves = (ctas + tl.sms - 1) / tl.sms;
+      // efficiency of the wave schedule, with a mild preference for >= 2 waves and for fewer, longer CTAs
+      double eff = (double)ctas / (double)(waves * tl.sms);
+      if (ipc < 32 && sp > 1) eff *= 0.9;                       // very short CTAs: prologue (Q load, TMEM alloc) shows
+      if (eff > best + 1e-9) { best = eff; splits = real; }
+    }
+  }
   p.img_per_cta = (p.bc + splits - 1) / splits;
   splits = (p.bc + p.img_per_cta - 1) / p.img_per_cta;
   DAMSM_REQUIRE(rows <= 2147483647 && splits <= 65535, "tensor-core launch: grid too large");
@@ -864,8 +882,24 @@ static int tc_launch(const TcLaunch &tl, TcParams &p, int64_t rows, cudaStream_t
   return check_launch(BWD ? "words_bwd_tc (fused recompute)" : "words_fwd_tc");
 }
 
-int launch_hmat_tc(const void *x_a, const float *svec, int64_t bc, int64_t r, int64_t kc, float alpha, float *hmat,
-                   cudaStream_t st);   // hmat_tc.cu
+int launch_hmat_tc(const void *x_a, const float *svec, int64_t bc, int64_t r, int64_t kc, const float *alpha_dev,
+                   float *hmat, cudaStream_t st);   // hmat_tc.cu
+
+// Device scalars of one backward call (head of the workspace): normalised upstream gradients, their magnitude, and
+// the epilogue scales that undo the fp16 scaling of the scratch rows.
+constexpr int64_t TC_SCAL_BYTES = 256;
+__global__ void bwd_scalars_kernel(const float *__restrict__ g, float inv_ds, float inv_ba, float *__restrict__ out) {
+  const float g0 = g[0], g1 = g[1];
+  const float gm = fmaxf(fabsf(g0), fabsf(g1));
+  const bool ok = gm > 0.f && gm < INFINITY;
+  out[0] = ok ? g0 / gm : 0.f;
+  out[1] = ok ? g1 / gm : 0.f;
+  out[2] = ok ? gm : 0.f;
+  out[3] = ok ? inv_ds * gm : 0.f;   // alpha of the dvhat / dqhat GEMMs
+  out[4] = ok ? inv_ba * gm : 0.f;   // alpha of the H kernel
+  out[5] = 1.f;
+  out[6] = 0.f;
+}
 
 static cublasHandle_t get_cublas() {
   static thread_local cublasHandle_t h = nullptr;
@@ -913,8 +947,8 @@ extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void
   TcParams p{};
   p.br = (int)br; p.bc = (int)bc; p.T = (int)t; p.R = (int)r; p.D = (int)d;
   p.g1 = gamma1; p.g2 = gamma2; p.g3 = gamma3; p.mask = mask; p.unorm = unorm; p.sim = sim; p.stats = stats;
-  p.dbg = getenv("DAMSM_DBG") ? atoi(getenv("DAMSM_DBG")) : 0;
 #ifdef DAMSM_TC_DEBUG
+  p.dbg = getenv("DAMSM_DBG") ? atoi(getenv("DAMSM_DBG")) : 0;
   if (getenv("DAMSM_TRACE")) {
     static long long *tr = nullptr;
     if (!tr) cudaMalloc(&tr, 3 * 16 * 8 * sizeof(long long));
@@ -937,6 +971,8 @@ extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void
 }
 
 // bytes of scratch per caption row of a chunk: two fp16 matrices [(j,r)][t_pad] + the per-word scales (bc, t_pad) fp32
+extern "C" int64_t damsm_words_bwd_tc_fixed_bytes(void) { return TC_SCAL_BYTES; }
+
 extern "C" int64_t damsm_words_bwd_tc_row_bytes(int64_t bc, int64_t t, int64_t r) {
   const int64_t tp = (t + 7) / 8 * 8;
   return 2 * tp * bc * r * 2 + tp * bc * 4;
@@ -960,16 +996,17 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
   int rc;
   if ((rc = tc_prepare(&tl, "words_bwd_tc", qhat16, q_rows, vhat16, gx, br, bc, t, r, d))) return rc;
   const int64_t row_bytes = damsm_words_bwd_tc_row_bytes(bc, t, r);
-  int64_t chunk = workspace_bytes / row_bytes;
-  DAMSM_REQUIRE(chunk >= 1, "words_bwd_tc: workspace of %lld B is smaller than one caption row (%lld B)",
-                (long long)workspace_bytes, (long long)row_bytes);
-  if (chunk > br) chunk = br;
-  if (chunk > 2 && (chunk & 1)) --chunk;      // even chunks: pairs of caption rows run as 2-CTA clusters
+  const int64_t max_chunk = (workspace_bytes - TC_SCAL_BYTES) / row_bytes;
+  DAMSM_REQUIRE(max_chunk >= 1, "words_bwd_tc: workspace of %lld B is smaller than one caption row (%lld B + %lld B)",
+                (long long)workspace_bytes, (long long)row_bytes, (long long)TC_SCAL_BYTES);
+  // equal chunks (no short tail chunk), even row counts (pairs of caption rows can run as 2-CTA clusters)
+  const int64_t n_chunks = (br + max_chunk - 1) / max_chunk;
+  int64_t chunk = (br + n_chunks - 1) / n_chunks;
+  if ((chunk & 1) && chunk < max_chunk) ++chunk;
   cudaStream_t st = (cudaStream_t)stream;
   cublasHandle_t h = get_cublas();
   DAMSM_REQUIRE(h != nullptr, "words_bwd_tc: cublasCreate failed");
   DAMSM_CUBLAS(cublasSetStream(h, st));
-  const float one = 1.f, zero = 0.f;
   const int64_t n_rows = bc * r;
   // Typical magnitudes: dS ~ gamma3/(B T) x [1e-3, 14],  b A ~ gamma3/(B T) x [1e-3, 200].  Scale both by a
   // power of two so that they sit in the middle of fp16's normal range [6e-5, 65504] (stores saturate), and undo
@@ -977,40 +1014,55 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
   const float lb = rintf(log2f((float)b_total * (float)t / fmaxf(gamma3, 1e-3f)));
   const float scale_ds = exp2f(lb + 6.f), scale_ba = exp2f(lb + 4.f);
   const float inv_ds = 1.f / scale_ds, inv_ba = 1.f / scale_ba;
+  float *scal = reinterpret_cast<float *>(workspace);
+  uint8_t *ws = reinterpret_cast<uint8_t *>(workspace) + TC_SCAL_BYTES;
+  bwd_scalars_kernel<<<1, 1, 0, st>>>(gscale, inv_ds, inv_ba, scal);
+  if ((rc = check_launch("words_bwd_tc (scalars)"))) return rc;
   for (int64_t i0 = 0; i0 < br; i0 += chunk) {
     const int64_t bi = (br - i0 < chunk) ? (br - i0) : chunk;
     const int64_t kc = bi * tp;
-    __half *x_ds = (__half *)workspace;
+    __half *x_ds = (__half *)ws;
     __half *x_a = x_ds + n_rows * kc;
     float *svec = reinterpret_cast<float *>(x_a + n_rows * kc);
     TcParams p{};
     p.br = (int)br; p.bc = (int)bc; p.T = (int)t; p.R = (int)r; p.D = (int)d;
     p.g1 = gamma1; p.g2 = gamma2; p.g3 = gamma3; p.mask = mask; p.unorm = unorm; p.sim = const_cast<float *>(sim);
     p.stats = const_cast<float *>(stats);
-    p.i0 = (int)i0; p.tp = (int)tp; p.kc = kc; p.row_lse = row_lse; p.col_lse = col_lse; p.gscale = gscale;
+    p.i0 = (int)i0; p.tp = (int)tp; p.kc = kc; p.row_lse = row_lse; p.col_lse = col_lse; p.gscale = scal;
     p.labels = labels; p.row_offset = row_offset; p.b_total = b_total; p.kq = kq;
     p.x_ds = x_ds; p.x_a = hmat ? x_a : nullptr; p.svec = svec; p.scale_ds = scale_ds; p.scale_ba = scale_ba;
+#ifdef DAMSM_TC_DEBUG
     p.dbg = getenv("DAMSM_DBG") ? atoi(getenv("DAMSM_DBG")) : 0;
+#endif
     if ((rc = tc_launch<true>(tl, p, bi, st))) return rc;
-    if (getenv("DAMSM_BWD_FUSED_ONLY")) continue;   // bench.py times the fused recompute kernel alone this way
+#ifdef DAMSM_TC_DEBUG
+    // development builds only: time the fused recompute kernel alone / stop after it (results are then incomplete)
+    if (getenv("DAMSM_BWD_FUSED_ONLY")) continue;
     if (getenv("DAMSM_DEBUG_SYNC")) {
       cudaError_t e = cudaStreamSynchronize(st);
       fprintf(stderr, "damsm debug: fused bwd kernel chunk i0=%lld done: %s\n", (long long)i0, cudaGetErrorString(e));
       if (getenv("DAMSM_DEBUG_SKIP_GEMM")) continue;
     }
+#endif
     const __half *qc = (const __half *)qhat16 + i0 * tp * d;
+    // alpha / beta are device scalars (the upstream-gradient magnitude is only known on the device)
+    DAMSM_CUBLAS(cublasSetPointerMode(h, CUBLAS_POINTER_MODE_DEVICE));
+    cublasStatus_t s1 = CUBLAS_STATUS_SUCCESS, s2 = CUBLAS_STATUS_SUCCESS;
     // dvhat (bc*R x D) += X_dS (bc*R x kc) . qhat_chunk (kc x D)            [row-major view; cuBLAS is column-major]
     if (dvhat)
-      DAMSM_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)d, (int)n_rows, (int)kc, &inv_ds, qc, CUDA_R_16F,
-                                (int)d, x_ds, CUDA_R_16F, (int)kc, &one, dvhat, CUDA_R_32F, (int)d, CUBLAS_COMPUTE_32F,
-                                CUBLAS_GEMM_DEFAULT_TENSOR_OP));
+      s1 = cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)d, (int)n_rows, (int)kc, scal + 3, qc, CUDA_R_16F, (int)d, x_ds,
+                        CUDA_R_16F, (int)kc, scal + 5, dvhat, CUDA_R_32F, (int)d, CUBLAS_COMPUTE_32F,
+                        CUBLAS_GEMM_DEFAULT_TENSOR_OP);
     // dqhat_chunk (kc x D) = X_dS^T (kc x bc*R) . vhat (bc*R x D)
     if (dqhat)
-      DAMSM_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, (int)d, (int)kc, (int)n_rows, &inv_ds, vhat16, CUDA_R_16F,
-                                (int)d, x_ds, CUDA_R_16F, (int)kc, &zero, dqhat + i0 * tp * d, CUDA_R_32F, (int)d,
-                                CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT_TENSOR_OP));
+      s2 = cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, (int)d, (int)kc, (int)n_rows, scal + 3, vhat16, CUDA_R_16F, (int)d,
+                        x_ds, CUDA_R_16F, (int)kc, scal + 6, dqhat + i0 * tp * d, CUDA_R_32F, (int)d, CUBLAS_COMPUTE_32F,
+                        CUBLAS_GEMM_DEFAULT_TENSOR_OP);
+    cublasSetPointerMode(h, CUBLAS_POINTER_MODE_HOST);
+    DAMSM_CUBLAS(s1);
+    DAMSM_CUBLAS(s2);
     // H_j (R x R) += sum_k s_k A_j[:,k] A_j[:,k]^T: own tcgen05 kernel (hmat_tc.cu), one CTA per image
-    if (hmat && (rc = launch_hmat_tc(x_a, svec, bc, r, kc, inv_ba, hmat, st))) return rc;
+    if (hmat && (rc = launch_hmat_tc(x_a, svec, bc, r, kc, scal + 4, hmat, st))) return rc;
   }
   return 0;
 }

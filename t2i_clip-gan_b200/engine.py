@@ -26,7 +26,35 @@ def _require_cuda(*tensors):
                 "DAMSM kernels are CUDA-only (sm_100a); got a CPU tensor and there is no CPU fallback")
 
 
-class CudaEngine:
+def _on_tensor_device(fn):
+    """Run an engine method with the device of its first CUDA tensor argument current: the C ABI launches on the
+    CURRENT device's stream, so a caller that holds tensors of another device (``cuda:1`` while ``cuda:0`` is
+    current) would otherwise launch on the wrong GPU."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kw):
+        for a in list(args) + list(kw.values()):
+            if isinstance(a, dict):
+                a = next((v for v in a.values() if torch.is_tensor(v) and v.is_cuda), None)
+            if torch.is_tensor(a) and a.is_cuda:
+                if a.device.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(a.device):
+                    return fn(self, *args, **kw)
+        return fn(self, *args, **kw)
+    return wrapped
+
+
+class _EngineMeta(type):
+    def __new__(mcls, name, bases, ns):
+        for k, v in list(ns.items()):
+            if callable(v) and not k.startswith("_") or k == "_words_bwd_tc":
+                ns[k] = _on_tensor_device(v)
+        return super().__new__(mcls, name, bases, ns)
+
+
+class CudaEngine(metaclass=_EngineMeta):
     """Exact-fp32 SIMT path (precision='fp32') and bf16 tcgen05 path (precision='bf16')."""
 
     name = "cuda"
@@ -149,19 +177,32 @@ class CudaEngine:
         return dqhat, dvhat, hmat, kq
 
     # scratch for the tensor-core backward: the fused kernel + GEMMs run chunk by chunk inside it.  Larger chunks
-    # mean fewer launches and a longer K for the gradient GEMMs; default = a third of the free HBM, at least 6 GiB.
+    # mean fewer launches and a longer K for the gradient GEMMs; default = a third of the HBM that is free at the
+    # FIRST call with a given shape (at least 6 GiB, never more than 80 % of what is free), remembered per shape so
+    # that the chunking -- and with it the launch geometry -- does not drift from iteration to iteration.
     tc_workspace_bytes = None
+    _tc_ws_rows = {}
+
+    def _tc_workspace(self, dev, br, bc, t, r):
+        lib = _lib.load()
+        row_bytes = lib.damsm_words_bwd_tc_row_bytes(bc, t, r)
+        fixed = lib.damsm_words_bwd_tc_fixed_bytes()
+        key = (dev.index, br, bc, t, r, self.tc_workspace_bytes)
+        rows = self._tc_ws_rows.get(key)
+        if rows is None:
+            budget = self.tc_workspace_bytes
+            if budget is None:
+                free = torch.cuda.mem_get_info(dev)[0]
+                budget = min(max(6 << 30, free // 3), int(free * 0.8))
+            rows = int(min(max(1, (budget - fixed) // row_bytes), br))
+            self._tc_ws_rows[key] = rows
+        return fixed + rows * row_bytes, rows
 
     def _words_bwd_tc(self, qhat16, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
                       row_offset, b_total, gammas, br, bc, t, r, d, need_dq=True, need_dv=True):
         dev = qhat16.device
         tp = qhat16.shape[1]
-        lib = _lib.load()
-        row_bytes = lib.damsm_words_bwd_tc_row_bytes(bc, t, r)
-        budget = self.tc_workspace_bytes
-        if budget is None:
-            budget = max(6 << 30, torch.cuda.mem_get_info(dev)[0] // 3)
-        ws_bytes = min(max(row_bytes, budget // row_bytes * row_bytes), row_bytes * br)
+        ws_bytes, ws_rows = self._tc_workspace(dev, br, bc, t, r)
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         dqhat = torch.empty((br, tp, d), device=dev, dtype=torch.float32) if need_dq else None
         dvhat = torch.zeros((bc, r, d), device=dev, dtype=torch.float32) if need_dv else None
@@ -173,9 +214,9 @@ class CudaEngine:
                   _lib.ptr(labels), gscale.data_ptr(), int(row_offset), int(b_total), br, bc, t, r, d,
                   float(gammas[0]), float(gammas[1]), float(gammas[2]), ws.data_ptr(), ws_bytes,
                   _lib.ptr(dqhat), _lib.ptr(dvhat), _lib.ptr(hmat), kq.data_ptr(), _stream())
-        chunks = -(-br // max(1, ws_bytes // row_bytes))
-        # own kernels per chunk: fused recompute + hmat (cuBLAS not counted)
-        _lib.add_launches((2 if need_dv else 1) * chunks - 1)
+        chunks = -(-br // ws_rows)
+        # own kernels: the scalar kernel + per chunk the fused recompute and hmat (cuBLAS not counted)
+        _lib.add_launches((2 if need_dv else 1) * chunks)
         return (dqhat[:, :t, :] if need_dq else None), dvhat, hmat, kq
 
     # ---- masked bidirectional cross-entropy ---------------------------------------------------------------
