@@ -10,10 +10,10 @@ NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xco
 all: $(OUT)
 
 $(OUT): $(SRC) $(HDR)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRC) -lcublas -Xlinker -rpath=/usr/local/cuda/lib64
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRC)
 
 ptxas-info:
-	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o /tmp/damsm_ptxas.so $(SRC) -lcublas 2>&1 | grep -E "Compiling|registers|spill" 
+	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o /tmp/damsm_ptxas.so $(SRC) 2>&1 | grep -E "Compiling|registers|spill" 
 
 clean:
 	rm -f $(OUT)

@@ -95,6 +95,18 @@ DAMSM_API int damsm_words_bwd_f32(const float *qhat, const float *vhat, const fl
 /* host: dynamic shared memory the fused fp32 pair kernel needs for (T,R); <0 if unsupported */
 DAMSM_API int64_t damsm_words_f32_smem_bytes(int64_t t, int64_t r);
 
+/* Dense contraction on the tensor cores (own persistent tcgen05 kernel, csrc/gemm_tc.cu; no library GEMM):
+ *   C (m x n, fp32, pitch ldc)  =|+=  alpha * alpha_dev[0] * A (m x k) . B (k x n)
+ * a_mn = 0: A is stored (m, k) row-major with pitch lda;  a_mn = 1: stored (k, m) row-major (i.e. A^T as it lies).
+ * b_mn = 0: B is stored (n, k) row-major with pitch ldb;  b_mn = 1: stored (k, n) row-major.
+ * fmt: 0 fp16, 1 bf16, 2 fp32 multiplied as TF32.  accumulate = 1 adds to C.  alpha_dev may be NULL.
+ * Serves the backward of the reference's two torch.bmm (losses.py:117, :182-183: dvhat += dS^T qhat, dqhat = dS vhat)
+ * and of linear_subr (nn.Linear, model.py:21,46,78: dx = dy W, dW = dy^T x).  Rows of A and B must start on 16-byte
+ * boundaries. */
+DAMSM_API int damsm_gemm_tc(const void *a, int64_t lda, int a_mn, const void *b, int64_t ldb, int b_mn, int fmt,
+                            int64_t m, int64_t n, int64_t k, float alpha, const float *alpha_dev, int accumulate,
+                            float *c, int64_t ldc, void *stream);
+
 /* ---- tensor-core path (tcgen05 / TMEM / TMA) for the bf16-input configurations; same math as
  * damsm_words_fwd_f32.  All MMA operands are bounded (|qhat|,|vhat|,|G| <= 1, e2 in [1, e^gamma1]), so they are
  * staged as fp16 -- same kind::f16 tensor rate as bf16 with 3 more mantissa bits -- and accumulated in fp32.

@@ -6,10 +6,11 @@
 // largest tensor of the loss is never re-read from HBM between the projection and the pair kernels.
 // X (B*(R+1), K) and W (N, K) are consumed in place by TMA: fp32 operands run as kind::tf32 (no conversion pass),
 // bf16 operands as kind::f16.  One CTA per 128 rows of X (CLS rows are computed and discarded: 1/(R+1) of the work).
-// Roofline: tensor; algorithmic flops 2*B*R*K*N.  The backward is three plain GEMMs (cuBLAS) + a column sum.
-#include <cublas_v2.h>
+// Roofline: tensor; algorithmic flops 2*B*R*K*N.  The backward is two contractions on the own tcgen05 GEMM (gemm_tc.cu,
+// TF32 operands read in place) + a column sum.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "gemm_tc.cuh"
 
 namespace damsm {
 using namespace tc;
@@ -211,12 +212,6 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ x
   atomicAdd(out + c, s);
 }
 
-static cublasHandle_t pj_cublas() {
-  static thread_local cublasHandle_t h = nullptr;
-  if (!h && cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) h = nullptr;
-  return h;
-}
-
 }  // namespace damsm
 
 using namespace damsm;
@@ -262,26 +257,21 @@ extern "C" int damsm_project_regions_bwd(const float *x, int64_t b, int64_t r, i
   DAMSM_REQUIRE(x && w && dy && work, "project_regions_bwd: null pointer");
   if (b == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  cublasHandle_t h = pj_cublas();
-  DAMSM_REQUIRE(h != nullptr, "project_regions_bwd: cublasCreate failed");
-  DAMSM_REQUIRE(cublasSetStream(h, st) == CUBLAS_STATUS_SUCCESS, "project_regions_bwd: cublasSetStream failed");
-  const float one = 1.f, zero = 0.f;
   const int64_t rows = b * (r + 1);
   const size_t pitch = sizeof(float) * (size_t)((r + 1) * n);
   DAMSM_CUDA(cudaMemset2DAsync(work, pitch, 0, sizeof(float) * (size_t)n, (size_t)b, st));
   DAMSM_CUDA(cudaMemcpy2DAsync(work + n, pitch, dy, sizeof(float) * (size_t)(r * n), sizeof(float) * (size_t)(r * n), (size_t)b,
                                cudaMemcpyDeviceToDevice, st));
-  if (dx) {   // dx (rows x K) = work (rows x N) . w (N x K)      [row-major; cuBLAS sees the transposes]
-    cublasStatus_t s = cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)k, (int)rows, (int)n, &one, w, CUDA_R_32F, (int)k, work,
-                                    CUDA_R_32F, (int)n, &zero, dx, CUDA_R_32F, (int)k, CUBLAS_COMPUTE_32F_FAST_TF32,
-                                    CUBLAS_GEMM_DEFAULT_TENSOR_OP);
-    DAMSM_REQUIRE(s == CUBLAS_STATUS_SUCCESS, "project_regions_bwd: dx GEMM failed (%d)", (int)s);
+  GemmTcArgs g{};
+  g.fmt = 2; g.alpha = 1.f; g.alpha_dev = nullptr; g.accumulate = 0; g.allow_split_k = 1;
+  int rc;
+  if (dx) {   // dx (rows x K) = work (rows x N) . w (N x K): A as stored (K-major), B = w as stored (k_gemm = N rows, MN-major)
+    g.a = work; g.lda = n; g.a_mn = 0; g.b = w; g.ldb = k; g.b_mn = 1; g.m = rows; g.n = k; g.k = n; g.c = dx; g.ldc = k;
+    if ((rc = launch_gemm_tc(g, st))) return rc;
   }
-  if (dw) {   // dw (N x K) = work^T (N x rows) . x (rows x K)
-    cublasStatus_t s = cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, (int)k, (int)n, (int)rows, &one, x, CUDA_R_32F, (int)k, work,
-                                    CUDA_R_32F, (int)n, &zero, dw, CUDA_R_32F, (int)k, CUBLAS_COMPUTE_32F_FAST_TF32,
-                                    CUBLAS_GEMM_DEFAULT_TENSOR_OP);
-    DAMSM_REQUIRE(s == CUBLAS_STATUS_SUCCESS, "project_regions_bwd: dw GEMM failed (%d)", (int)s);
+  if (dw) {   // dw (N x K) = work^T (N x rows) . x (rows x K): both operands MN-major (k_gemm = rows)
+    g.a = work; g.lda = n; g.a_mn = 1; g.b = x; g.ldb = k; g.b_mn = 1; g.m = n; g.n = k; g.k = rows; g.c = dw; g.ldc = k;
+    if ((rc = launch_gemm_tc(g, st))) return rc;
   }
   if (db) {
     DAMSM_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * n, st));

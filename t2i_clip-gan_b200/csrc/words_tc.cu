@@ -10,7 +10,7 @@
 //   regs   N'_t = sum_r e2 S, NN_t = sum_r e2 M'  (warp butterfly + shared memory across warps)
 //          rho_t = (N'/Y) / (max(sqrt(NN)/Y, eps) max(u_t, eps)),  sim = gamma3/gamma2 log sum_t exp(gamma2 rho_t)
 //   bwd    the same recompute, then dS = a A + P (dP - W), dP = gamma1 A (a S - b M), W = sum_t P dP; dS and A leave
-//          the chip as scaled fp16 rows that two plain GEMMs (cuBLAS: dvhat, dqhat) and hmat_tc.cu (H) contract per chunk.
+//          the chip as scaled fp16 rows that the own tcgen05 GEMM (gemm_tc.cu: dvhat, dqhat) and hmat_tc.cu (H) contract per chunk.
 //
 // Regions live on the MMA M axis (TMEM lanes): the softmax over words, its backward column term and every
 // per-region quantity are then thread-local, and the accumulators (NT columns per tile) leave TMEM room for a
@@ -19,11 +19,11 @@
 // producer and the MMA issuer are warps 7 and 15 (which own no region row when R+1 <= 224) or two extra warps 16/17.
 // Forward launches pair the CTAs of two captions into a cluster that shares the image stream by TMA multicast.
 // Budgets and the roofline are in DESIGN.md.
-#include <cublas_v2.h>
 #include <stdlib.h>
 #include <type_traits>
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "gemm_tc.cuh"
 
 namespace damsm {
 using namespace tc;
@@ -901,20 +901,6 @@ __global__ void bwd_scalars_kernel(const float *__restrict__ g, float inv_ds, fl
   out[6] = 0.f;
 }
 
-static cublasHandle_t get_cublas() {
-  static thread_local cublasHandle_t h = nullptr;
-  if (!h && cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) h = nullptr;
-  return h;
-}
-#define DAMSM_CUBLAS(call)                                                    \
-  do {                                                                        \
-    cublasStatus_t s__ = (call);                                              \
-    if (s__ != CUBLAS_STATUS_SUCCESS) {                                       \
-      ::damsm::set_error("%s failed: cublas status %d", #call, (int)s__);     \
-      return 4;                                                               \
-    }                                                                         \
-  } while (0)
-
 }  // namespace damsm
 
 using namespace damsm;
@@ -1004,9 +990,6 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
   int64_t chunk = (br + n_chunks - 1) / n_chunks;
   if ((chunk & 1) && chunk < max_chunk) ++chunk;
   cudaStream_t st = (cudaStream_t)stream;
-  cublasHandle_t h = get_cublas();
-  DAMSM_REQUIRE(h != nullptr, "words_bwd_tc: cublasCreate failed");
-  DAMSM_CUBLAS(cublasSetStream(h, st));
   const int64_t n_rows = bc * r;
   // Typical magnitudes: dS ~ gamma3/(B T) x [1e-3, 14],  b A ~ gamma3/(B T) x [1e-3, 200].  Scale both by a
   // power of two so that they sit in the middle of fp16's normal range [6e-5, 65504] (stores saturate), and undo
@@ -1045,22 +1028,23 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
     }
 #endif
     const __half *qc = (const __half *)qhat16 + i0 * tp * d;
-    // alpha / beta are device scalars (the upstream-gradient magnitude is only known on the device)
-    DAMSM_CUBLAS(cublasSetPointerMode(h, CUBLAS_POINTER_MODE_DEVICE));
-    cublasStatus_t s1 = CUBLAS_STATUS_SUCCESS, s2 = CUBLAS_STATUS_SUCCESS;
-    // dvhat (bc*R x D) += X_dS (bc*R x kc) . qhat_chunk (kc x D)            [row-major view; cuBLAS is column-major]
-    if (dvhat)
-      s1 = cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)d, (int)n_rows, (int)kc, scal + 3, qc, CUDA_R_16F, (int)d, x_ds,
-                        CUDA_R_16F, (int)kc, scal + 5, dvhat, CUDA_R_32F, (int)d, CUBLAS_COMPUTE_32F,
-                        CUBLAS_GEMM_DEFAULT_TENSOR_OP);
+    // The two gradient contractions of the chunk on the own tcgen05 GEMM (gemm_tc.cu); the scratch rows, qhat and vhat
+    // are read in place (K-major / MN-major operands); alpha is a device scalar (it carries the upstream-gradient
+    // magnitude, which is only known on the device).
+    GemmTcArgs g{};
+    g.fmt = 0; g.alpha = 1.f; g.alpha_dev = scal + 3; g.allow_split_k = 1;
+    // dvhat (bc*R x D) += X_dS (bc*R x kc) . qhat_chunk (kc x D)
+    if (dvhat) {
+      g.a = x_ds; g.lda = kc; g.a_mn = 0; g.b = qc; g.ldb = d; g.b_mn = 1;
+      g.m = n_rows; g.n = d; g.k = kc; g.accumulate = 1; g.c = dvhat; g.ldc = d;
+      if ((rc = launch_gemm_tc(g, st))) return rc;
+    }
     // dqhat_chunk (kc x D) = X_dS^T (kc x bc*R) . vhat (bc*R x D)
-    if (dqhat)
-      s2 = cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, (int)d, (int)kc, (int)n_rows, scal + 3, vhat16, CUDA_R_16F, (int)d,
-                        x_ds, CUDA_R_16F, (int)kc, scal + 6, dqhat + i0 * tp * d, CUDA_R_32F, (int)d, CUBLAS_COMPUTE_32F,
-                        CUBLAS_GEMM_DEFAULT_TENSOR_OP);
-    cublasSetPointerMode(h, CUBLAS_POINTER_MODE_HOST);
-    DAMSM_CUBLAS(s1);
-    DAMSM_CUBLAS(s2);
+    if (dqhat) {
+      g.a = x_ds; g.lda = kc; g.a_mn = 1; g.b = vhat16; g.ldb = d; g.b_mn = 1;
+      g.m = kc; g.n = d; g.k = n_rows; g.accumulate = 0; g.c = dqhat + i0 * tp * d; g.ldc = d;
+      if ((rc = launch_gemm_tc(g, st))) return rc;
+    }
     // H_j (R x R) += sum_k s_k A_j[:,k] A_j[:,k]^T: own tcgen05 kernel (hmat_tc.cu), one CTA per image
     if (hmat && (rc = launch_hmat_tc(x_a, svec, bc, r, kc, scal + 4, hmat, st))) return rc;
   }

@@ -215,9 +215,32 @@ class CudaEngine(metaclass=_EngineMeta):
                   float(gammas[0]), float(gammas[1]), float(gammas[2]), ws.data_ptr(), ws_bytes,
                   _lib.ptr(dqhat), _lib.ptr(dvhat), _lib.ptr(hmat), kq.data_ptr(), _stream())
         chunks = -(-br // ws_rows)
-        # own kernels: the scalar kernel + per chunk the fused recompute and hmat (cuBLAS not counted)
-        _lib.add_launches((2 if need_dv else 1) * chunks)
+        # own kernels: the scalar kernel (counted by the call) + per chunk the fused recompute, the dvhat GEMM and the
+        # H kernel (image side), the dqhat GEMM (caption side)
+        _lib.add_launches((1 + (2 if need_dv else 0) + (1 if need_dq else 0)) * chunks)
         return (dqhat[:, :t, :] if need_dq else None), dvhat, hmat, kq
+
+    # ---- dense contraction on the tensor cores (gemm_tc.cu) ----------------------------------------------------
+    def gemm_tc(self, a, b, a_mn=False, b_mn=False, out=None, accumulate=False, alpha=1.0, alpha_dev=None):
+        """C (M, N) fp32 =|+= alpha * A . B.  ``a``: (M, K) row-major, or with ``a_mn`` (K, M) row-major (A^T as it
+        lies); ``b``: (N, K) row-major, or with ``b_mn`` (K, N) row-major.  fp16 / bf16 operands, or fp32 (as TF32)."""
+        _require_cuda(a, b, out, alpha_dev)
+        if a.dtype != b.dtype or a.dtype not in _DTYPE_CODE:
+            raise TypeError("gemm_tc: operands must share a dtype (fp16, bf16 or fp32)")
+        if a.dim() != 2 or b.dim() != 2 or a.stride(1) != 1 or b.stride(1) != 1:
+            raise ValueError("gemm_tc: operands must be 2-D with a contiguous last dimension")
+        m, k = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+        n, kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+        if kb != k:
+            raise ValueError(f"gemm_tc: K mismatch ({k} vs {kb})")
+        if out is None:
+            if accumulate:
+                raise ValueError("gemm_tc: accumulate needs an output tensor")
+            out = torch.empty((m, n), device=a.device, dtype=torch.float32)
+        fmt = {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}[a.dtype]
+        _lib.call("damsm_gemm_tc", a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn), fmt,
+                  m, n, k, float(alpha), _lib.ptr(alpha_dev), int(accumulate), out.data_ptr(), out.stride(0), _stream())
+        return out
 
     # ---- masked bidirectional cross-entropy ---------------------------------------------------------------
     def ce_stats(self, logits, cls_rows, cls_cols, row_offset):
@@ -327,6 +350,7 @@ class CudaEngine(metaclass=_EngineMeta):
         db = torch.empty(n, device=dev, dtype=torch.float32) if need_db else None
         _lib.call("damsm_project_regions_bwd", x32.data_ptr(), b, rp1 - 1, k, w32.data_ptr(), n, dy.data_ptr(),
                   work.data_ptr(), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _stream())
+        _lib.add_launches(int(need_dx) + int(need_dw) + int(need_db) - 1)      # two GEMM launches + the column sum
         return dx, dw, db
 
     # ---- rm_special_token (pretrain_DAMSM.py:58-79) ------------------------------------------------------------
