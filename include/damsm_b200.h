@@ -118,35 +118,68 @@ DAMSM_API int64_t damsm_words_tc_gx_cols(int64_t r);
 DAMSM_API int damsm_gram_pack_tc(const float *gram, int64_t bc, int64_t r, void *gx, void *stream);
 /* host: dynamic shared memory of the tcgen05 kernel for (T,R,D); <0 if the shape is unsupported */
 DAMSM_API int64_t damsm_words_tc_smem_bytes(int64_t t, int64_t r, int64_t d);
+/* Skip-padded-words plan.  A padded word (mask 0) gets softmax-over-words weight 0, attends uniformly over the regions
+ * (losses.py:127,173-174), its context is the image's mean region and its cosine is ONE dot product -- it still enters
+ * the score and receives gradient (losses.py:198-203 sum over ALL words), but it does not need the pair kernels.
+ * nw[i] = the number of word columns the pair kernels compute for caption i: the smallest multiple of 16 covering the
+ * last unmasked word (clamped to [16, NT]); every word t >= nw[i] is padding and is handled in closed form by
+ * damsm_pad_terms_fwd / _bwd.  order[] = the captions sorted by nw, longest first.  Both (br) int32, device. */
+DAMSM_API int damsm_words_tc_plan(const uint8_t *mask, int64_t br, int64_t t, int32_t *nw, int32_t *order, void *stream);
 /* q_rows = rows per caption in qhat16 (T, or T padded to a multiple of 8 with zero rows).
  * stats (br, bc, 3, T) fp32 or NULL: per pair and word the cosine rho_t, ||c_t|| and 1/Y_t that the backward
- * needs (12*T bytes per pair; B^2*T, not B^2*T*R). */
+ * needs (12*T bytes per pair; B^2*T, not B^2*T*R; only words t < nw[i] are written).
+ * nw / order (damsm_words_tc_plan) and epad (br, bc) = sum over the skipped words of exp(gamma2 rho_bar)
+ * (damsm_pad_terms_fwd) may all be NULL: every caption then computes all its words. */
 DAMSM_API int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
-                                 const float *unorm, const uint8_t *mask, int64_t br, int64_t bc, int64_t t,
+                                 const float *unorm, const uint8_t *mask, const int32_t *nw, const int32_t *order,
+                                 const float *epad, int64_t br, int64_t bc, int64_t t,
                                  int64_t r, int64_t d, float gamma1, float gamma2, float gamma3, float *sim,
                                  float *stats, void *stream);
 /* Backward of the tensor-core path.  A fused tcgen05 kernel recomputes S, P, A, M per pair on chip (the per-word
- * scalars come from `stats` written by damsm_words_fwd_tc) and emits
- * dS, A and diag(b)A as (scaled) fp16 into `workspace`, one chunk of caption rows at a time
- * (damsm_words_bwd_tc_row_bytes() bytes per caption row; at least one row must fit); three plain GEMMs per
- * chunk (cuBLAS, fp16 in / fp32 accumulate) then contract them with qhat / vhat / each other:
- *   dvhat (bc,R,D) += dS^T qhat   [ACCUMULATED, caller zeroes]     dqhat (br,q_rows,D) = dS vhat   [OVERWRITTEN]
+ * scalars come from `stats` written by damsm_words_fwd_tc) and emits dS and A as (scaled) fp16 rows
+ * [(image, region)][(caption, word)] into `workspace`, one chunk of captions at a time; the K index (caption, word) is
+ * RAGGED: caption at sorted position s owns columns [koff[s], koff[s+1]) with koff the prefix sums of nw[order[s]]
+ * (device AND host copies; the host copy sizes the launches).  chunk_pos_host[0..n_chunks] are the chunk boundaries as
+ * positions in the sorted order; a chunk needs fixed_bytes + (koff[s1] - koff[s0]) * col_bytes of workspace.  Per chunk
+ * the own tcgen05 GEMM (damsm_gemm_tc) contracts the rows with the packed word rows / vhat, and hmat_tc with each other:
+ *   dvhat (bc,R,D) += dS^T qhat   [ACCUMULATED, caller zeroes]     dqpack (koff[br], D) = dS vhat  [OVERWRITTEN, packed rows]
  *   hmat (bc,R,R) += A^T diag(b) A [ACCUMULATED]                   kq (br,T)                       [ACCUMULATED]
- * qhat16 must be padded: q_rows == T rounded up to a multiple of 8. */
-DAMSM_API int64_t damsm_words_bwd_tc_row_bytes(int64_t bc, int64_t t, int64_t r);
+ * qpack16 (koff[br], D) fp16 is scratch for the packed word rows.  damsm_pad_terms_bwd then unpacks dqpack into
+ * dqhat (br, q_rows, D) and adds the gradients of the skipped words. */
+DAMSM_API int64_t damsm_words_bwd_tc_col_bytes(int64_t bc, int64_t r);
 /* Bytes at the head of `workspace` that hold the device scalars of one call (the upstream gradients g0, g1 normalised
- * by max(|g0|,|g1|), that maximum, and the epilogue scales): workspace_bytes >= fixed + rows * row_bytes.  The fp16
- * range of the scratch rows therefore does not depend on the loss weight (`(w_loss0 + w_loss1) * LAMBDA`,
- * losses.py:355; an AMP loss scale). */
+ * by max(|g0|,|g1|), that maximum, and the epilogue scales).  The fp16 range of the scratch rows therefore does not
+ * depend on the loss weight (`(w_loss0 + w_loss1) * LAMBDA`, losses.py:355; an AMP loss scale). */
 DAMSM_API int64_t damsm_words_bwd_tc_fixed_bytes(void);
 DAMSM_API int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
-                                   const float *unorm, const uint8_t *mask, const float *sim, const float *stats,
+                                   const float *unorm, const uint8_t *mask, const int32_t *nw, const int32_t *order,
+                                   const int64_t *koff, const int64_t *koff_host, const int64_t *chunk_pos_host,
+                                   int64_t n_chunks, const float *sim, const float *stats,
                                    const float *row_lse, const float *col_lse, const int64_t *labels,
                                    const float *gscale,
                                    int64_t row_offset, int64_t b_total, int64_t br, int64_t bc, int64_t t, int64_t r,
                                    int64_t d, float gamma1, float gamma2, float gamma3, void *workspace,
-                                   int64_t workspace_bytes, float *dqhat, float *dvhat, float *hmat, float *kq,
-                                   void *stream);
+                                   int64_t workspace_bytes, void *qpack16, float *dqpack, float *dvhat, float *hmat,
+                                   float *kq, void *stream);
+/* Closed form of the skipped (padded) words (oracle/padded_closed_form.py; losses.py:127,173-174,182,197-203).
+ * Forward: vbar_j = mean_r vhat_jr (fp32 + fp16 copies), nbar_j = |vbar_j|, rn_j = 1/max(nbar_j, 1e-6), and
+ *   epad[i][j] = sum_{t >= nw[i], t < T} exp(gamma2 * vbar_j.qhat_it / (max(nbar_j,1e-6) max(u_it,1e-6)))
+ * as one tcgen05 GEMM (vbar16 x qhat16^T) whose epilogue does the exp-sum.
+ * Backward: the same GEMM with an epilogue that writes coef[j][(i,t)] = scale * dL/drho_bar / (n u) (fp16, `coef`
+ * (bc, br*tp) scratch), two GEMMs  dqpad = coef^T vbar  and  dvbar = coef qhat,  then
+ *   dqhat[i][t] = dqpack[koff[s]+t] (t < nw)  |  dqpad[i][t] (nw <= t < T)  |  0;   kq[i][t] += qhat_it . dqpad_it
+ *   dvhat[j][r] += (dvbar_j - (vbar_j . dvbar_j) vbar_j / nbar_j^2) / R          (added to every region row)
+ * dqhat or dvhat may be NULL (that side is skipped).  scal: 256 B of device scratch. */
+DAMSM_API int damsm_pad_terms_fwd(const void *vhat16, const void *qhat16, const float *unorm, const int32_t *nw,
+                                  int64_t br, int64_t bc, int64_t t, int64_t tp, int64_t r, int64_t d, float gamma2,
+                                  float *vbar32, void *vbar16, float *nbar, float *rn, float *epad, void *stream);
+DAMSM_API int damsm_pad_terms_bwd(const float *vbar32, const void *vbar16, const float *nbar, const float *rn,
+                                  const void *qhat16, const float *qhat32, const float *unorm, const int32_t *nw,
+                                  const int32_t *order, const int64_t *koff, const float *sim, const float *row_lse,
+                                  const float *col_lse, const int64_t *labels, const float *gscale, int64_t row_offset,
+                                  int64_t b_total, int64_t br, int64_t bc, int64_t t, int64_t tp, int64_t r, int64_t d,
+                                  float gamma2, float gamma3, void *coef, float *dqpad, float *dvbar, float *scal,
+                                  const float *dqpack, float *dqhat, float *kq, float *dvhat, void *stream);
 
 /* ---- class_ids masking + both CrossEntropyLoss() (losses.py:55-66,84-88 / :224-232,256-269) -----------
  * logits (br,bc) row block of the (b_total x b_total) matrix.  In place: logits[i][j] = -inf where

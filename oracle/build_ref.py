@@ -3,7 +3,7 @@
 The reference (``/root/reference``) is pure Python and does not exist on the GPU box.  To let ``bench.py``'s
 ``cpu_baseline`` leg and ``bench.py --impl reference`` time the UNMODIFIED reference there (``cpu_baseline.kind ==
 "reference"``) instead of a port, this script byte-compiles the reference files the hot path needs, from where they
-lie, into ``oracle/_ref/`` (sourceless ``.pyc`` modules: build outputs only -- ``oracle/_ref/`` is git-ignored and no
+lie, into ``oracle/_ref/`` (byte-code files ``<module>.refbc``: build outputs only -- ``oracle/_ref/`` is git-ignored and no
 reference source is copied into the repository; the directory travels to the GPU box like the built ``.so``).
 
     python oracle/build_ref.py        # needs /root/reference; a no-op (exit 0) where it is absent
@@ -31,7 +31,8 @@ def build(verbose: bool = True) -> bool:
             print("oracle/build_ref: reference sources not present at", SRC_ROOT, "- nothing to do")
         return False
     for rel in FILES:
-        dst = os.path.join(OUT_ROOT, rel + "c")                     # sourceless module: <name>.pyc beside nothing
+        # byte code only; not named *.pyc because tools that snapshot the tree (gpurun) drop those
+        dst = os.path.join(OUT_ROOT, rel[:-3] + ".refbc")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")                          # GlobalAttention.py:1 has an invalid escape sequence

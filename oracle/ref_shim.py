@@ -27,7 +27,7 @@ BUILT_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 def _built_ok() -> bool:
     tag = os.path.join(BUILT_ROOT, "PYTHON_TAG")
-    return (os.path.isfile(os.path.join(BUILT_ROOT, "miscc", "losses.pyc")) and os.path.isfile(tag)
+    return (os.path.isfile(os.path.join(BUILT_ROOT, "miscc", "losses.refbc")) and os.path.isfile(tag)
             and open(tag).read().strip() == sys.implementation.cache_tag)
 
 
@@ -59,6 +59,28 @@ class _EasyDict(dict):
     __setitem__ = __setattr__
 
 
+class _ByteCodeFinder:
+    """Meta-path finder for the byte-compiled reference modules under oracle/_ref (``<module>.refbc``)."""
+    NAMES = {"miscc": "miscc/__init__", "miscc.config": "miscc/config", "miscc.losses": "miscc/losses",
+             "GlobalAttention": "GlobalAttention", "nt_xent": "nt_xent", "masks": "masks"}
+
+    def __init__(self, root):
+        self.root = root
+
+    def find_spec(self, name, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        rel = self.NAMES.get(name)
+        if rel is None:
+            return None
+        file = os.path.join(self.root, rel + ".refbc")
+        if not os.path.isfile(file):
+            return None
+        loader = importlib.machinery.SourcelessFileLoader(name, file)
+        return importlib.util.spec_from_file_location(
+            name, file, loader=loader, submodule_search_locations=[os.path.join(self.root, "miscc")] if name == "miscc" else None)
+
+
 _mods = None
 
 
@@ -76,7 +98,11 @@ def load():
     # the reference's package is called ``miscc`` -- make sure ours is not shadowing it
     for name in [k for k in sys.modules if k == "miscc" or k.startswith("miscc.") or k == "GlobalAttention"]:
         del sys.modules[name]
-    sys.path.insert(0, REF_ROOT)
+    finder = _ByteCodeFinder(REF_ROOT) if REF_ROOT == BUILT_ROOT else None
+    if finder:
+        sys.meta_path.insert(0, finder)
+    else:
+        sys.path.insert(0, REF_ROOT)
     try:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
@@ -84,7 +110,10 @@ def load():
             from miscc import losses              # noqa: E402
             from miscc.config import cfg          # noqa: E402
     finally:
-        sys.path.remove(REF_ROOT)
+        if finder:
+            sys.meta_path.remove(finder)
+        else:
+            sys.path.remove(REF_ROOT)
     # keep them out of sys.modules so the product's own ``miscc`` drop-in can be imported later
     for name in [k for k in sys.modules if k == "miscc" or k.startswith("miscc.") or k == "GlobalAttention"]:
         del sys.modules[name]
@@ -174,7 +203,13 @@ def ref_nt_xent(z_i, z_j, temperature):
     mods = []
     for name in ("nt_xent", "masks"):
         path = os.path.join(REF_ROOT, name + ".py")
-        spec = importlib.util.spec_from_file_location("_ref_" + name, path if os.path.isfile(path) else path + "c")
+        if os.path.isfile(path):
+            spec = importlib.util.spec_from_file_location("_ref_" + name, path)
+        else:
+            import importlib.machinery
+            bc = os.path.join(REF_ROOT, name + ".refbc")
+            spec = importlib.util.spec_from_file_location("_ref_" + name, bc,
+                                                          loader=importlib.machinery.SourcelessFileLoader("_ref_" + name, bc))
         m = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(m)
         mods.append(m)

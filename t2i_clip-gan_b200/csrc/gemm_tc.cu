@@ -5,7 +5,8 @@
 // Every operand is consumed IN PLACE through 2-D TMA with the 128-byte swizzle, in whichever of its two storage
 // orders it already has -- the UMMA shared-memory descriptor then names the matching canonical layout:
 //   A stored (M, K) row-major = "K-major"    box = 256 rows x 128 B of k                 (SBO 1024)
-//   A stored (K, M) row-major = "MN-major"   boxes of 64|32 k-rows x 128 B of m, 4|8 per 256 rows (LBO = box bytes, SBO 1024)
+//   A stored (K, M) row-major = "MN-major"   boxes of 64|32 k-rows x 128 B of m, 4|8 per 256 rows (LBO = box bytes, SBO 1024;
+//                                            fp32: the 32-byte-atom swizzle, SBO 512 -- the only MN-major TF32 layout)
 //   B stored (N, K) row-major = "K-major",   B stored (K, N) row-major = "MN-major"     likewise with N = 256.
 // That is what lets the backward of the two bmm's (autograd of losses.py:117 and :182-183) read the fp16 scratch rows,
 // qhat and vhat as they lie:   dvhat += X_dS . qhat_chunk   (A K-major, B MN-major)
@@ -42,6 +43,8 @@ struct GemmTcParams {
   const float *alpha_dev;   // optional device scalar, multiplied with alpha
   float alpha;
   int mode;             // 0: C = v, 1: C += v (read-modify-write), 2: C += v with red.global.add (split-K)
+  int n_tile;           // columns per N tile (256; the padded-word epilogues use whole captions: cpt * tp <= 256)
+  PadEpilogue pad;      // EPI != 0
 };
 
 __device__ __forceinline__ void tma_load_2d_g(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1) {
@@ -51,15 +54,18 @@ __device__ __forceinline__ void tma_load_2d_g(void *smem_dst, const CUtensorMap 
                : "memory");
 }
 
-// Shared-memory matrix descriptor, 128-byte swizzle, 8-row groups 1024 B apart; `lbo_bytes` = distance between
-// adjacent 128-byte-wide MN chunks of an MN-major operand (unused for K-major operands).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+// Shared-memory matrix descriptor, 128-byte swizzle.  K-major operands and 16-bit MN-major operands use the 16-byte-atom
+// swizzle (layout type 2; 8-row groups, SBO = 1024 B); `lbo_bytes` = distance between adjacent 128-byte-wide MN chunks
+// of an MN-major operand (unused for K-major).  32-bit (TF32) MN-major operands exist only in the 32-byte-atom variant
+// of the 128-byte swizzle (layout type 1: the pattern repeats every 4 rows, SBO = 512 B) -- what TMA writes with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, bool base32 = false) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((base32 ? 512 : 1024) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(base32 ? 1 : 2) << 61;
   return d;
 }
 
@@ -84,8 +90,8 @@ __device__ __forceinline__ void gt_mma(uint32_t tmem_d, uint64_t da, uint64_t db
   }
 }
 
-// FMT: 0 fp16, 1 bf16, 2 tf32 (fp32 storage)
-template <int FMT>
+// FMT: 0 fp16, 1 bf16, 2 tf32 (fp32 storage); EPI: 0 store / accumulate C, 1 / 2 the padded-word epilogues (gemm_tc.cuh)
+template <int FMT, int EPI>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmTcParams p) {
   constexpr bool TF32 = FMT == 2;
@@ -122,11 +128,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int tn = item % p.tiles_n, tm = (item / p.tiles_n) % p.tiles_m, sp = item / (p.tiles_n * p.tiles_m);
         const int kb0 = sp * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
-        const int m0 = tm * GT_TILE, n0 = tn * GT_TILE;
+        const int m0 = tm * GT_TILE, n0 = tn * p.n_tile;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t *a = smem + stage * GT_STAGE_BYTES, *b = a + GT_OPER_BYTES;
-          mbar_arrive_expect_tx(&full[stage], GT_STAGE_BYTES);   // out-of-range parts of a box are zero-filled and counted
+          // out-of-range parts of a box are zero-filled and counted
+          mbar_arrive_expect_tx(&full[stage], GT_OPER_BYTES + (uint32_t)p.n_tile * 128u);
           if (p.a_mn) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) tma_load_2d_g(a + c * CH_BYTES, &tmA, &full[stage], m0 + c * CH, kb * KB);
@@ -146,12 +153,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
     if (elect_one()) {
-      const uint32_t idesc = gt_idesc(FMT, p.a_mn, p.b_mn, GT_TILE);
+      const uint32_t idesc = gt_idesc(FMT, p.a_mn, p.b_mn, p.n_tile);
       // per K = 16|8 step the start address moves by 32 B inside the 128-byte row (K-major) or by 16|8 k-rows of 128 B
       // (MN-major); the second M tile starts 128 rows (K-major) or 128/CH chunks (MN-major) further
       const uint32_t a_kstep = p.a_mn ? (uint32_t)(TF32 ? 8 : 16) * 128 : 32, b_kstep = p.b_mn ? (uint32_t)(TF32 ? 8 : 16) * 128 : 32;
       const uint32_t a_tile1 = p.a_mn ? (uint32_t)(128 / CH) * CH_BYTES : 128u * 128u;
       const uint32_t a_lbo = p.a_mn ? CH_BYTES : 16u, b_lbo = p.b_mn ? CH_BYTES : 16u;   // K-major + swizzle: LBO unused
+      const bool a32 = TF32 && p.a_mn, b32 = TF32 && p.b_mn;                              // 32-byte-atom swizzle
       int stage = 0, phase = 0, n_done = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
         const int sp = item / (p.tiles_n * p.tiles_m);
@@ -164,10 +172,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t a0 = smem_u32(smem + stage * GT_STAGE_BYTES), b0 = a0 + GT_OPER_BYTES;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t db = umma_desc_sw128(b0 + k * b_kstep, b_lbo);
+            const uint64_t db = umma_desc_sw128(b0 + k * b_kstep, b_lbo, b32);
             const bool acc = (kb > kb0) || (k > 0);
-            gt_mma<TF32>(tmem_base, umma_desc_sw128(a0 + k * a_kstep, a_lbo), db, idesc, acc);
-            gt_mma<TF32>(tmem_base + GT_TILE, umma_desc_sw128(a0 + a_tile1 + k * a_kstep, a_lbo), db, idesc, acc);
+            gt_mma<TF32>(tmem_base, umma_desc_sw128(a0 + k * a_kstep, a_lbo, a32), db, idesc, acc);
+            gt_mma<TF32>(tmem_base + GT_TILE, umma_desc_sw128(a0 + a_tile1 + k * a_kstep, a_lbo, a32), db, idesc, acc);
           }
           umma_commit(&empty[stage]);
           if (++stage == GT_STAGES) { stage = 0; phase ^= 1; }
@@ -178,61 +186,147 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===================================== epilogue (warps 2-5) =====================================
     const int quad = warp & 3;                                      // TMEM lane quadrant this warp may read
-    const float alpha = p.alpha * (p.alpha_dev ? *p.alpha_dev : 1.f);
-    int n_done = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
-      const int tn = item % p.tiles_n, tm = (item / p.tiles_n) % p.tiles_m, sp = item / (p.tiles_n * p.tiles_m);
-      const bool has_k = sp * p.kb_per_split < p.nkb;
-      mbar_wait(acc_full, n_done & 1);
-      tc_fence_after();
+    if constexpr (EPI == 0) {
+      const float alpha = p.alpha * (p.alpha_dev ? *p.alpha_dev : 1.f);
+      int n_done = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+        const int tn = item % p.tiles_n, tm = (item / p.tiles_n) % p.tiles_m, sp = item / (p.tiles_n * p.tiles_m);
+        const bool has_k = sp * p.kb_per_split < p.nkb;
+        mbar_wait(acc_full, n_done & 1);
+        tc_fence_after();
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        const int64_t row = (int64_t)tm * GT_TILE + half * 128 + quad * 32 + lane;
-        const bool row_ok = row < p.M;
-        float *crow = p.c + (row_ok ? row : 0) * p.ldc + (int64_t)tn * GT_TILE;
-        const int ncols = (int)min((int64_t)GT_TILE, p.N - (int64_t)tn * GT_TILE);
-        const uint32_t t0 = tmem_base + (((uint32_t)quad * 32) << 16) + half * GT_TILE;
+        for (int half = 0; half < 2; ++half) {
+          const int64_t row = (int64_t)tm * GT_TILE + half * 128 + quad * 32 + lane;
+          const bool row_ok = row < p.M;
+          float *crow = p.c + (row_ok ? row : 0) * p.ldc + (int64_t)tn * GT_TILE;
+          const int ncols = (int)min((int64_t)GT_TILE, p.N - (int64_t)tn * GT_TILE);
+          const uint32_t t0 = tmem_base + (((uint32_t)quad * 32) << 16) + half * GT_TILE;
 #pragma unroll 1
-        for (int c = 0; c < GT_TILE; c += 32) {                      // warp-uniform trip count: tcgen05.ld is collective
-          if (c >= ncols) break;
-          float x[32];
-          tmem_ld16(t0 + c, x);
-          tmem_ld16(t0 + c + 16, x + 16);
-          if (!row_ok || !has_k) continue;
-          if (c + 32 <= ncols && (((uintptr_t)(crow + c)) & 15) == 0) {
-            float4 *q = reinterpret_cast<float4 *>(crow + c);
-            if (p.mode == 0) {
+          for (int c = 0; c < GT_TILE; c += 32) {                      // warp-uniform trip count: tcgen05.ld is collective
+            if (c >= ncols) break;
+            float x[32];
+            tmem_ld16(t0 + c, x);
+            tmem_ld16(t0 + c + 16, x + 16);
+            if (!row_ok || !has_k) continue;
+            if (c + 32 <= ncols && (((uintptr_t)(crow + c)) & 15) == 0) {
+              float4 *q = reinterpret_cast<float4 *>(crow + c);
+              if (p.mode == 0) {
 #pragma unroll
-              for (int k = 0; k < 8; ++k) q[k] = make_float4(alpha * x[4 * k], alpha * x[4 * k + 1], alpha * x[4 * k + 2], alpha * x[4 * k + 3]);
-            } else if (p.mode == 1) {
-              float4 o[8];                                           // all eight loads in flight before the first use
+                for (int k = 0; k < 8; ++k) q[k] = make_float4(alpha * x[4 * k], alpha * x[4 * k + 1], alpha * x[4 * k + 2], alpha * x[4 * k + 3]);
+              } else if (p.mode == 1) {
+                float4 o[8];                                           // all eight loads in flight before the first use
 #pragma unroll
-              for (int k = 0; k < 8; ++k) o[k] = q[k];
+                for (int k = 0; k < 8; ++k) o[k] = q[k];
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                o[k].x = fmaf(alpha, x[4 * k], o[k].x); o[k].y = fmaf(alpha, x[4 * k + 1], o[k].y);
-                o[k].z = fmaf(alpha, x[4 * k + 2], o[k].z); o[k].w = fmaf(alpha, x[4 * k + 3], o[k].w);
-                q[k] = o[k];
+                for (int k = 0; k < 8; ++k) {
+                  o[k].x = fmaf(alpha, x[4 * k], o[k].x); o[k].y = fmaf(alpha, x[4 * k + 1], o[k].y);
+                  o[k].z = fmaf(alpha, x[4 * k + 2], o[k].z); o[k].w = fmaf(alpha, x[4 * k + 3], o[k].w);
+                  q[k] = o[k];
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) atomicAdd(crow + c + k, alpha * x[k]);
               }
             } else {
 #pragma unroll
-              for (int k = 0; k < 32; ++k) atomicAdd(crow + c + k, alpha * x[k]);
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              if (c + k < ncols) {
-                if (p.mode == 0) crow[c + k] = alpha * x[k];
-                else if (p.mode == 1) crow[c + k] = fmaf(alpha, x[k], crow[c + k]);
-                else atomicAdd(crow + c + k, alpha * x[k]);
+              for (int k = 0; k < 32; ++k) {
+                if (c + k < ncols) {
+                  if (p.mode == 0) crow[c + k] = alpha * x[k];
+                  else if (p.mode == 1) crow[c + k] = fmaf(alpha, x[k], crow[c + k]);
+                  else atomicAdd(crow + c + k, alpha * x[k]);
+                }
               }
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
+    } else {
+      // ---- closed form of the skipped (padded) words: image = accumulator row = thread, a caption's words on
+      //      consecutive columns (gemm_tc.cuh) ----
+      const PadEpilogue &e = p.pad;
+      const float g2l = e.g2 * 1.4426950408889634f;
+      int n_done = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+        const int tn = item % p.tiles_n, tm = item / p.tiles_n;
+        mbar_wait(acc_full, n_done & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int64_t j = (int64_t)tm * GT_TILE + half * 128 + quad * 32 + lane;     // image
+          const bool j_ok = j < e.bc;
+          const float rn = j_ok ? e.rn[j] : 0.f;
+          const uint32_t t0 = tmem_base + (((uint32_t)quad * 32) << 16) + half * GT_TILE;
+          float cl = 0.f;
+          int64_t lj = 0;
+          if (EPI == 2 && j_ok) { cl = e.col_lse[j]; lj = e.labels ? e.labels[j] : j; }
+#pragma unroll 1
+          for (int c = 0; c < e.cpt; ++c) {
+            const int64_t i = (int64_t)tn * e.cpt + c;                                   // caption (warp-uniform)
+            if (i >= e.br) break;
+            const int nwi = e.nw[i];
+            const float *un = e.unorm + i * e.T;
+            if constexpr (EPI == 1) {
+              float acc = 0.f;
+              for (int t = nwi; t < e.T; t += 8) {                                       // nw is a multiple of 16
+                float x[8];
+                tmem_ld8(t0 + c * e.tp + t, x);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  if (t + k < e.T) {
+                    const float rho = x[k] * rn / fmaxf(un[t + k], kCosEps);
+                    acc += exp2f(g2l * rho);
+                  }
+                }
+              }
+              if (j_ok) e.epad[i * e.bc + j] = acc;
+            } else {
+              // dL/dsim_ij from both cross-entropies (losses.py:265-269), exactly as the pair kernels rebuild it
+              float g = 0.f, lse = 0.f;
+              if (j_ok) {
+                const float sv = e.sim[i * e.bc + j];
+                if (sv != -INFINITY) {
+                  const int64_t gi = e.row_offset + i;
+                  const int64_t li = e.labels ? e.labels[gi] : gi;
+                  const float gr = __expf(sv - e.row_lse[i]) - (li == j ? 1.f : 0.f);
+                  const float gc = __expf(sv - cl) - (lj == gi ? 1.f : 0.f);
+                  g = (e.gscale[0] * gr + e.gscale[1] * gc) / (float)e.b_total;
+                  lse = sv * (e.g2 / e.g3);
+                }
+              }
+              __half *crow = e.coef + (j_ok ? j : 0) * (e.br * e.tp) + i * e.tp;
+              const float gk = g * e.g3 * rn * e.scale;
+              for (int t = 0; t < e.tp; t += 8) {
+                uint32_t pk[4] = {0u, 0u, 0u, 0u};
+                if (t + 8 > nwi && t < e.T) {                                            // warp-uniform
+                  float x[8], a[8];
+                  tmem_ld8(t0 + c * e.tp + t, x);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    a[k] = 0.f;
+                    if (t + k >= nwi && t + k < e.T) {
+                      const float ru = 1.f / fmaxf(un[t + k], kCosEps);
+                      const float rho = x[k] * rn * ru;
+                      a[k] = gk * ru * __expf(e.g2 * rho - lse);                        // scale * beta / (n u)
+                    }
+                  }
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const __half2 h = __floats2half2_rn(a[2 * k], a[2 * k + 1]);
+                    pk[k] = *reinterpret_cast<const uint32_t *>(&h);
+                  }
+                }
+                if (j_ok) *reinterpret_cast<uint4 *>(crow + t) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+      }
     }
   }
   tc_fence_before();
@@ -246,7 +340,7 @@ typedef CUresult (*PFN_encodeTiledG)(CUtensorMap *, CUtensorMapDataType, cuuint3
 
 // 2-D row-major tensor (outer, inner) with `pitch` elements between rows; box = (box_outer rows, 128 bytes), 128B swizzle
 static int gt_make_map(CUtensorMap *m, const void *base, int fmt, uint64_t inner, uint64_t outer, uint64_t pitch,
-                       uint32_t box_outer) {
+                       uint32_t box_outer, bool atom32 = false) {
   static PFN_encodeTiledG enc = nullptr;
   if (!enc) {
     void *ptr = nullptr;
@@ -264,7 +358,8 @@ static int gt_make_map(CUtensorMap *m, const void *base, int fmt, uint64_t inner
   cuuint32_t box[2] = {128 / es, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DAMSM_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu pitch=%llu", (int)r,
                 (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch);
   return 0;
@@ -287,6 +382,7 @@ int launch_gemm_tc(const GemmTcArgs &g, cudaStream_t st) {
   p.tiles_n = (int)((g.n + GT_TILE - 1) / GT_TILE);
   p.a_mn = g.a_mn ? 1 : 0; p.b_mn = g.b_mn ? 1 : 0;
   p.c = g.c; p.ldc = g.ldc; p.alpha_dev = g.alpha_dev; p.alpha = g.alpha;
+  p.n_tile = GT_TILE;
   int dev = 0, sms = 0;
   DAMSM_CUDA(cudaGetDevice(&dev));
   DAMSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -308,23 +404,63 @@ int launch_gemm_tc(const GemmTcArgs &g, cudaStream_t st) {
   }
   CUtensorMap tmA, tmB;
   int rc;
-  if (p.a_mn) { if ((rc = gt_make_map(&tmA, g.a, g.fmt, (uint64_t)g.m, (uint64_t)g.k, (uint64_t)g.lda, (uint32_t)kbe))) return rc; }
+  if (p.a_mn) { if ((rc = gt_make_map(&tmA, g.a, g.fmt, (uint64_t)g.m, (uint64_t)g.k, (uint64_t)g.lda, (uint32_t)kbe, g.fmt == 2))) return rc; }
   else        { if ((rc = gt_make_map(&tmA, g.a, g.fmt, (uint64_t)g.k, (uint64_t)g.m, (uint64_t)g.lda, GT_TILE))) return rc; }
-  if (p.b_mn) { if ((rc = gt_make_map(&tmB, g.b, g.fmt, (uint64_t)g.n, (uint64_t)g.k, (uint64_t)g.ldb, (uint32_t)kbe))) return rc; }
+  if (p.b_mn) { if ((rc = gt_make_map(&tmB, g.b, g.fmt, (uint64_t)g.n, (uint64_t)g.k, (uint64_t)g.ldb, (uint32_t)kbe, g.fmt == 2))) return rc; }
   else        { if ((rc = gt_make_map(&tmB, g.b, g.fmt, (uint64_t)g.k, (uint64_t)g.n, (uint64_t)g.ldb, GT_TILE))) return rc; }
   const int64_t items = tiles * p.splits;
   const unsigned grid = (unsigned)(items < sms ? items : sms);
   const uint32_t smem = GT_STAGES * GT_STAGE_BYTES + 256 + 1024;
 #define DAMSM_LAUNCH_GT(F_)                                                                                        \
   do {                                                                                                             \
-    DAMSM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    gemm_tc_kernel<F_><<<grid, GT_THREADS, smem, st>>>(tmA, tmB, p);                                               \
+    DAMSM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<F_, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    gemm_tc_kernel<F_, 0><<<grid, GT_THREADS, smem, st>>>(tmA, tmB, p);                                             \
   } while (0)
   if (g.fmt == 0) DAMSM_LAUNCH_GT(0);
   else if (g.fmt == 1) DAMSM_LAUNCH_GT(1);
   else DAMSM_LAUNCH_GT(2);
 #undef DAMSM_LAUNCH_GT
   return check_launch("gemm_tc");
+}
+
+// vbar16 (bc, d) fp16, qhat16 (br * tp, d) fp16 (tp zero-padded word rows per caption); see PadEpilogue (gemm_tc.cuh)
+int launch_gemm_tc_pad(const void *vbar16, const void *qhat16, int64_t d, const PadEpilogue &e, cudaStream_t st) {
+  DAMSM_REQUIRE(vbar16 && qhat16 && e.nw && e.unorm && e.rn, "gemm_tc_pad: null pointer");
+  DAMSM_REQUIRE(e.mode == 1 || e.mode == 2, "gemm_tc_pad: mode %d", e.mode);
+  DAMSM_REQUIRE(d % 8 == 0 && e.tp % 8 == 0 && e.tp >= e.T && e.tp <= GT_TILE, "gemm_tc_pad: bad shape d=%lld tp=%d T=%d",
+                (long long)d, e.tp, e.T);
+  if (e.br == 0 || e.bc == 0) return 0;
+  GemmTcParams p{};
+  p.pad = e;
+  int cpt = GT_TILE / e.tp;                          // whole captions per N tile, N a multiple of 16
+  while (cpt > 1 && (cpt * e.tp) % 16) --cpt;
+  DAMSM_REQUIRE((cpt * e.tp) % 16 == 0, "gemm_tc_pad: tp=%d cannot be tiled", e.tp);
+  p.pad.cpt = cpt;
+  p.n_tile = cpt * e.tp;
+  p.M = e.bc; p.N = e.br * e.tp;
+  p.nkb = (int)((d + 63) / 64);
+  p.kb_per_split = p.nkb; p.splits = 1;
+  p.tiles_m = (int)((e.bc + GT_TILE - 1) / GT_TILE);
+  p.tiles_n = (int)((e.br + cpt - 1) / cpt);
+  p.a_mn = 0; p.b_mn = 0;
+  int dev = 0, sms = 0;
+  DAMSM_CUDA(cudaGetDevice(&dev));
+  DAMSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = gt_make_map(&tmA, vbar16, 0, (uint64_t)d, (uint64_t)e.bc, (uint64_t)d, GT_TILE))) return rc;
+  if ((rc = gt_make_map(&tmB, qhat16, 0, (uint64_t)d, (uint64_t)(e.br * e.tp), (uint64_t)d, (uint32_t)p.n_tile))) return rc;
+  const int64_t items = (int64_t)p.tiles_m * p.tiles_n;
+  const unsigned grid = (unsigned)(items < sms ? items : sms);
+  const uint32_t smem = GT_STAGES * GT_STAGE_BYTES + 256 + 1024;
+  if (e.mode == 1) {
+    DAMSM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_tc_kernel<0, 1><<<grid, GT_THREADS, smem, st>>>(tmA, tmB, p);
+  } else {
+    DAMSM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_tc_kernel<0, 2><<<grid, GT_THREADS, smem, st>>>(tmA, tmB, p);
+  }
+  return check_launch("gemm_tc_pad");
 }
 
 }  // namespace damsm

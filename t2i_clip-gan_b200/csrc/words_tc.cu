@@ -83,12 +83,18 @@ struct TcParams {
   float g1, g2, g3;
   const uint8_t *mask;
   const float *unorm;
+  // Per-caption word counts (skip-padded-words): the kernels compute words t < nw[i] (a multiple of 16 covering the last
+  // unmasked word); every word t >= nw[i] is padding, attends uniformly, and is handled in closed form (pad_terms.cu).
+  const int *nw;       // (br) or NULL = every caption uses all NT columns
+  const int *order;    // (br) caption processed by CTA row x (captions sorted by nw, longest first) or NULL = identity
+  const float *epad;   // forward: (br, bc) sum over the skipped words of exp(gamma2 rho_bar), or NULL
   float *sim;          // forward: out (br, bc); backward: in (masked, gamma3-scaled)
   float *stats;        // (br, bc, 3, T): rho, ||c||, 1/Y per word; forward writes (may be NULL), backward reads
   // ---- backward only ----
-  int i0;              // first caption row of this chunk (blockIdx.x is relative to it)
-  int tp;              // T padded to a multiple of 8: words per caption in the scratch matrices
-  int64_t kc;          // scratch row length = chunk_rows * tp
+  int i0;              // first position (in `order`) of this chunk (blockIdx.x is relative to it)
+  const int64_t *koff; // (br + 1) prefix sums of nw over the sorted captions: scratch column of caption position s
+  int64_t kbase;       // koff[i0]: first scratch column of the chunk
+  int64_t kc;          // scratch row length of this chunk = koff[i0 + rows] - koff[i0]
   const float *row_lse, *col_lse;
   const float *gscale;                // device scalars: [0],[1] = g0,g1 / max(|g0|,|g1|); [2] = that maximum
   const int64_t *labels;
@@ -182,6 +188,27 @@ __device__ __forceinline__ float warp_colsum(float (&v)[N], int lane) {
   return v[0];
 }
 
+// The per-thread word range [0, nh) (nh a multiple of 8, CTA-uniform) as column blocks of compile-time width and
+// offset for the transpose-reduce passes: 32-wide blocks first, then 16, then 8.
+#define DAMSM_TC_BLK(fn, W_, CB_)                                                                                   \
+  do {                                                                                                              \
+    if constexpr ((CB_) + (W_) <= NH) fn(std::integral_constant<int, (W_)>{}, std::integral_constant<int, (CB_)>{}); \
+  } while (0)
+#define DAMSM_TC_COLUMN_BLOCKS(fn)                                                         \
+  do {                                                                                     \
+    if (nh >= 32) {                                                                        \
+      DAMSM_TC_BLK(fn, 32, 0);                                                             \
+      if (nh >= 64) { DAMSM_TC_BLK(fn, 32, 32); }                                          \
+      else if (nh >= 48) { DAMSM_TC_BLK(fn, 16, 32); if (nh >= 56) DAMSM_TC_BLK(fn, 8, 48); } \
+      else if (nh >= 40) { DAMSM_TC_BLK(fn, 8, 32); }                                      \
+    } else if (nh >= 16) {                                                                 \
+      DAMSM_TC_BLK(fn, 16, 0);                                                             \
+      if (nh >= 24) DAMSM_TC_BLK(fn, 8, 16);                                               \
+    } else {                                                                               \
+      DAMSM_TC_BLK(fn, 8, 0);                                                              \
+    }                                                                                      \
+  } while (0)
+
 // NW = 16: the two softmax warps that own no region row (R+1 <= 224) serve as TMA producer (warp 7) and MMA
 // issuer (warp 15), 4 warps per scheduler and 128 registers per thread; NW = 18: two extra warps take those roles.
 // CL = 2: the CTAs of captions 2k and 2k+1 form a cluster and walk the same image sequence; each fetches one half of
@@ -221,7 +248,10 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float *zbuf = red2 + 24 * NT, *wbuf = zbuf + 1024;          // [2 parities][2 halves][256] each
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = (BWD ? p.i0 : 0) + blockIdx.x;
+  const int spos = (BWD ? p.i0 : 0) + blockIdx.x;                  // position in the sorted caption order
+  const int i = p.order ? p.order[spos] : spos;
+  const int NTi = p.nw ? p.nw[i] : NT;                             // word columns this caption computes (multiple of 16)
+  const int nh = NTi >> 1;                                         // ... per softmax thread (multiple of 8)
   const int j0 = blockIdx.y * p.img_per_cta;
   const int j1 = min(p.bc, j0 + p.img_per_cta);
   const int T = p.T, R = p.R;
@@ -261,7 +291,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t idesc = umma_idesc_f16(NT);
+  const uint32_t idesc = umma_idesc_f16(NTi);
   const uint32_t col_m = (uint32_t)(nbuf * L.tiles * NT);     // TMEM column of M'
 
   if (warp == TMA_WARP) {
@@ -384,7 +414,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int half = warp >> 3;                                     // which half of the words
     const int tile = (warp >> 2) & 1;
     const int rg = tile * 128 + (warp & 3) * 32 + lane;             // region row owned by this thread
-    const int c0 = half * NH;                                       // first word column owned by this thread
+    const int c0 = half * nh;                                       // first word column owned by this thread
     const uint32_t t_lane = tmem_base + (((uint32_t)(warp & 3) * 32) << 16) + tile * NT + c0;
     const uint32_t t_m = t_lane + col_m;
     const bool valid = rg < R;
@@ -400,7 +430,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float4 *tb4 = reinterpret_cast<const float4 *>(tb + c0);
     const float2 *tb22 = reinterpret_cast<const float2 *>(tb2 + c0);
     // cross-warp partial sums, laid out [parity][word t][8 warps of that word's half] so the tail reads float4s
-    float *red1w0 = red1 + (half * NH) * 8 + (warp & 7), *red2w0 = red2 + (half * NH) * 8 + (warp & 7);
+    float *red1w0 = red1 + c0 * 8 + (warp & 7), *red2w0 = red2 + c0 * 8 + (warp & 7);
     const int widx = (warp & 7) * 32 + lane;                        // row slot in zbuf / wbuf
     constexpr int CPL = (NT + 31) / 32;                             // words per lane in the one-warp sections
     // backward, warp 0: per-row constants of dL/dsim (both cross-entropies, losses.py:265-269)
@@ -429,11 +459,12 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float *st = p.stats ? p.stats + pair * 3 * T : nullptr;
       float xv[CPL];
       float mx = -INFINITY;
+      const int tmax = min(T, NTi);
 #pragma unroll
       for (int q = 0; q < CPL; ++q) {
         const int t = q * 32 + lane;
         xv[q] = -INFINITY;
-        if (t < T) {
+        if (t < tmax) {
           const float4 a0 = r1[2 * t], a1 = r1[2 * t + 1], b0 = r2[2 * t], b1 = r2[2 * t + 1];
           const float np = ((a0.x + a0.y) + (a0.z + a0.w)) + ((a1.x + a1.y) + (a1.z + a1.w));
           const float nn = ((b0.x + b0.y) + (b0.z + b0.w)) + ((b1.x + b1.y) + (b1.z + b1.w));
@@ -450,6 +481,8 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int q = 0; q < CPL; ++q) se += __expf(xv[q] - mx);       // exp(-inf) = 0 for the unused slots
       se = warp_sum(se);
+      // words t >= nw[i] (all padding): their exp(gamma2 rho_bar) sum comes from the closed form (|gamma2 rho| <= gamma2)
+      if (p.epad && NTi < T) se += p.epad[pair] * __expf(-mx);
       if (lane == 0) p.sim[pair] = p.g3 * ((__logf(se) + mx) / p.g2);
     };
     // ---- pass A of pair `it_`: e1 = exp(S + mask bias), Z = sum_t e1 (softmax over words, losses.py:127,143-144).
@@ -469,6 +502,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       } else
 #pragma unroll
       for (int c = 0; c < NH / 8; ++c) {
+        if (c * 8 >= nh) break;                                     // CTA-uniform: this caption has fewer word columns
         float x[8];
         tmem_ld<8>(ts_ + c * 8, x);
         const float4 ba = tb4[2 * c], bb = tb4[2 * c + 1];
@@ -518,6 +552,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int tl = 0; tl < NH; tl += 2) {
         if (DBG(p, 32)) break;
+        if (tl >= nh) break;
         const float2 bz = tb22[tl >> 1];
         const float a0 = ex2f(fmaf(e1[tl], k2, bz.x));
         const float a1 = ex2f(fmaf(e1[tl + 1], k2, bz.y));
@@ -548,17 +583,17 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t e1h[BWD ? NH / 2 : 1];
       if constexpr (BWD) {
 #pragma unroll
-        for (int k = 0; k < NH / 2; ++k) e1h[k] = pack_half2(e1[2 * k] * invZ, e1[2 * k + 1] * invZ);
+        for (int k = 0; k < NH / 2; ++k) {
+          if (2 * k >= nh) break;
+          e1h[k] = pack_half2(e1[2 * k] * invZ, e1[2 * k + 1] * invZ);
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(e2_ready);
       if constexpr (!BWD) {
         if (!DBG(p, 32)) {
-          if constexpr (NH >= 32) pass_b2(std::integral_constant<int, 32>{}, std::integral_constant<int, 0>{});
-          if constexpr (NH == 64) pass_b2(std::integral_constant<int, 32>{}, std::integral_constant<int, 32>{});
-          if constexpr (NH == 40) pass_b2(std::integral_constant<int, 8>{}, std::integral_constant<int, 32>{});
-          if constexpr (NH == 16) pass_b2(std::integral_constant<int, 16>{}, std::integral_constant<int, 0>{});
+          DAMSM_TC_COLUMN_BLOCKS(pass_b2);
         }
         tc_fence_before();
         __syncwarp();
@@ -580,21 +615,22 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           const float lse = (sv != -INFINITY) ? sv * (p.g2 / p.g3) : 0.f;   // sim = gamma3/gamma2 * lse
           const float *st = p.stats + pair * 3 * T;
+          float *svp = p.svec + (int64_t)j * p.kc + (p.koff[spos] - p.kbase);
 #pragma unroll
           for (int q = 0; q < CPL; ++q) {
             const int t = q * 32 + lane;
-            if (t < T) {
+            if (t < T && t < NTi) {
               const float rho = st[t], n = st[T + t], iy = st[2 * T + t];
               const float omega = __expf(p.g2 * rho - lse);
               const float beta = g * p.g3 * omega;                  // dL/drho_t
               const float a = beta / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
               const float bq = (n > kCosEps) ? beta * rho / (n * n) : 0.f;
               vcb[t] = make_float4(p.g1 * a * iy, p.g1 * bq * iy * iy, a * iy * p.scale_ds, 0.f);
-              p.svec[(int64_t)j * p.kc + (int64_t)blockIdx.x * p.tp + t] = bq * p.scale_ba;
+              svp[t] = bq * p.scale_ba;
               viyb[t] = iy;
               atomicAdd(p.kq + (int64_t)i * T + t, beta * rho * bw_gm);
-            } else if (t < p.tp) {
-              p.svec[(int64_t)j * p.kc + (int64_t)blockIdx.x * p.tp + t] = 0.f;
+            } else if (t < NTi) {
+              svp[t] = 0.f;
             }
           }
         }
@@ -632,10 +668,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (lane < W) red2w[(cbeg + lane) * 8] = cs;
         };
         if (!DBG(p, 32)) {
-        if constexpr (NH >= 32) pass_m(std::integral_constant<int, 32>{}, std::integral_constant<int, 0>{});
-        if constexpr (NH == 64) pass_m(std::integral_constant<int, 32>{}, std::integral_constant<int, 32>{});
-        if constexpr (NH == 40) pass_m(std::integral_constant<int, 8>{}, std::integral_constant<int, 32>{});
-        if constexpr (NH == 16) pass_m(std::integral_constant<int, 16>{}, std::integral_constant<int, 0>{});
+        DAMSM_TC_COLUMN_BLOCKS(pass_m);
         }
         tc_fence_before();
         __syncwarp();
@@ -652,6 +685,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float wp = 0.f;
 #pragma unroll
         for (int c = 0; c < NH / 8; ++c) {
+          if (c * 8 >= nh) break;
           float xs[8], xm[8];
           tmem_ld8_issue(t_s + c * 8, xs);
           tmem_ld8_issue(t_m + c * 8, xm);
@@ -672,13 +706,13 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // ---- dS = a A + P (dP - W); A; diag(b) A  -> scaled fp16 rows of the scratch matrices ----
         if (!DBG(p, 2)) {
           const int64_t row = (int64_t)j * R + (valid ? rg : 0);
-          const int64_t off = row * p.kc + (int64_t)blockIdx.x * p.tp + c0;
+          const int64_t off = row * p.kc + (p.koff[spos] - p.kbase) + c0;
           uint4 *o_ds = reinterpret_cast<uint4 *>(p.x_ds + off);
           uint4 *o_a = reinterpret_cast<uint4 *>(p.x_a + off);
           const float sp = p.scale_ds;
 #pragma unroll
           for (int c = 0; c < NH / 8; ++c) {
-            if (c0 + c * 8 < p.tp) {                                 // warp-uniform: tcgen05.ld is warp-collective
+            if (c * 8 < nh) {                                        // CTA-uniform: tcgen05.ld is warp-collective
               float xs[8], xm[8];
               tmem_ld8_issue(t_s + c * 8, xs);
               tmem_ld8_issue(t_m + c * 8, xm);
@@ -901,6 +935,56 @@ __global__ void bwd_scalars_kernel(const float *__restrict__ g, float inv_ds, fl
   out[6] = 0.f;
 }
 
+void launch_bwd_scalars(const float *gscale, float inv_ds, float inv_ba, float *out, cudaStream_t st) {
+  bwd_scalars_kernel<<<1, 1, 0, st>>>(gscale, inv_ds, inv_ba, out);
+}
+
+// ---- caption plan: per-caption word count nw[i] = ceil16(last unmasked word + 1) clamped to [16, NT], and the captions
+//      sorted by nw (longest first: CTAs of similar length run together, pairs of a 2-CTA cluster have equal counts and
+//      the longest work is scheduled first).  One CTA; counting sort over the <= 8 possible counts.
+__global__ void __launch_bounds__(1024) tc_plan_kernel(const uint8_t *__restrict__ mask, int br, int T, int NT,
+                                                       int *__restrict__ nw, int *__restrict__ order) {
+  __shared__ int cnt[9], start[9], cursor[9];
+  if (threadIdx.x < 9) cnt[threadIdx.x] = cursor[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < br; i += blockDim.x) {
+    int last = -1;
+    for (int t = 0; t < T; ++t)
+      if (mask[(int64_t)i * T + t]) last = t;
+    int n = ((last + 1 + 15) / 16) * 16;
+    n = n < 16 ? 16 : (n > NT ? NT : n);
+    nw[i] = n;
+    atomicAdd(&cnt[n >> 4], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 8; b >= 1; --b) { start[b] = acc; acc += cnt[b]; }
+  }
+  __syncthreads();
+  if (order) {
+    for (int i = threadIdx.x; i < br; i += blockDim.x) {
+      const int b = nw[i] >> 4;
+      order[start[b] + atomicAdd(&cursor[b], 1)] = i;
+    }
+  }
+}
+
+// qpack[(koff[s] + t)][:] = qhat16[order[s]][t][:] for t < nw (zero rows past the caption's q_rows): the word rows of the
+// sorted captions back to back, the K index of the scratch matrices
+__global__ void __launch_bounds__(128) tc_pack_q_kernel(const __half *__restrict__ qhat16, int q_rows, int d,
+                                                        const int *__restrict__ nw, const int *__restrict__ order,
+                                                        const int64_t *__restrict__ koff, __half *__restrict__ qpack) {
+  const int s = blockIdx.x, i = order[s], n = nw[i];
+  const int vec = d / 8;
+  const uint4 *src = reinterpret_cast<const uint4 *>(qhat16 + (int64_t)i * q_rows * d);
+  uint4 *dst = reinterpret_cast<uint4 *>(qpack + koff[s] * d);
+  for (int e = threadIdx.x; e < n * vec; e += blockDim.x) {
+    const int t = e / vec;
+    dst[e] = t < q_rows ? src[e] : make_uint4(0, 0, 0, 0);
+  }
+}
+
 }  // namespace damsm
 
 using namespace damsm;
@@ -921,8 +1005,18 @@ extern "C" int64_t damsm_words_tc_smem_bytes(int64_t t, int64_t r, int64_t d) {
   return tc_layout(nt, (int)r, (int)d).total;
 }
 
+extern "C" int damsm_words_tc_plan(const uint8_t *mask, int64_t br, int64_t t, int32_t *nw, int32_t *order, void *stream) {
+  DAMSM_REQUIRE(mask && nw, "words_tc_plan: null pointer");
+  const int nt = pick_nt((int)t);
+  DAMSM_REQUIRE(nt > 0, "words_tc_plan: T=%lld outside [1,128]", (long long)t);
+  if (br == 0) return 0;
+  tc_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(mask, (int)br, (int)t, nt, nw, order);
+  return check_launch("words_tc_plan");
+}
+
 extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
-                                  const float *unorm, const uint8_t *mask, int64_t br, int64_t bc, int64_t t, int64_t r,
+                                  const float *unorm, const uint8_t *mask, const int32_t *nw, const int32_t *order,
+                                  const float *epad, int64_t br, int64_t bc, int64_t t, int64_t r,
                                   int64_t d, float gamma1, float gamma2, float gamma3, float *sim, float *stats,
                                   void *stream) {
   DAMSM_REQUIRE(qhat16 && vhat16 && gx && unorm && mask && sim, "words_fwd_tc: null pointer");
@@ -933,6 +1027,7 @@ extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void
   TcParams p{};
   p.br = (int)br; p.bc = (int)bc; p.T = (int)t; p.R = (int)r; p.D = (int)d;
   p.g1 = gamma1; p.g2 = gamma2; p.g3 = gamma3; p.mask = mask; p.unorm = unorm; p.sim = sim; p.stats = stats;
+  p.nw = nw; p.order = order; p.epad = epad;
 #ifdef DAMSM_TC_DEBUG
   p.dbg = getenv("DAMSM_DBG") ? atoi(getenv("DAMSM_DBG")) : 0;
   if (getenv("DAMSM_TRACE")) {
@@ -956,39 +1051,32 @@ extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void
   return tc_launch<false>(tl, p, br, (cudaStream_t)stream);
 }
 
-// bytes of scratch per caption row of a chunk: two fp16 matrices [(j,r)][t_pad] + the per-word scales (bc, t_pad) fp32
 extern "C" int64_t damsm_words_bwd_tc_fixed_bytes(void) { return TC_SCAL_BYTES; }
 
-extern "C" int64_t damsm_words_bwd_tc_row_bytes(int64_t bc, int64_t t, int64_t r) {
-  const int64_t tp = (t + 7) / 8 * 8;
-  return 2 * tp * bc * r * 2 + tp * bc * 4;
-}
+// bytes of scratch per K column (= one word of one caption of a chunk): two fp16 matrices [(j,r)] + the per-word scales
+// (bc) fp32
+extern "C" int64_t damsm_words_bwd_tc_col_bytes(int64_t bc, int64_t r) { return 2 * bc * r * 2 + bc * 4; }
 
 extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
-                                  const float *unorm, const uint8_t *mask, const float *sim, const float *stats,
+                                  const float *unorm, const uint8_t *mask, const int32_t *nw, const int32_t *order,
+                                  const int64_t *koff, const int64_t *koff_host, const int64_t *chunk_pos_host,
+                                  int64_t n_chunks, const float *sim, const float *stats,
                                   const float *row_lse, const float *col_lse, const int64_t *labels,
                                   const float *gscale, int64_t row_offset,
                                   int64_t b_total, int64_t br, int64_t bc, int64_t t, int64_t r, int64_t d, float gamma1,
-                                  float gamma2, float gamma3, void *workspace, int64_t workspace_bytes, float *dqhat,
-                                  float *dvhat, float *hmat, float *kq, void *stream) {
+                                  float gamma2, float gamma3, void *workspace, int64_t workspace_bytes, void *qpack16,
+                                  float *dqpack, float *dvhat, float *hmat, float *kq, void *stream) {
   DAMSM_REQUIRE(qhat16 && vhat16 && gx && unorm && mask && sim && stats && row_lse && col_lse && gscale && workspace &&
-                    kq, "words_bwd_tc: null pointer");
+                    kq && nw && order && koff && koff_host && chunk_pos_host && qpack16,
+                "words_bwd_tc: null pointer");
   DAMSM_REQUIRE((dvhat == nullptr) == (hmat == nullptr), "words_bwd_tc: dvhat and hmat must be given together");
-  const int64_t tp = (t + 7) / 8 * 8;
-  DAMSM_REQUIRE(q_rows == tp, "words_bwd_tc: qhat16 must be padded to %lld rows per caption (got %lld)", (long long)tp,
-                (long long)q_rows);
   if (br == 0 || bc == 0) return 0;
+  DAMSM_REQUIRE(n_chunks >= 1 && chunk_pos_host[0] == 0 && chunk_pos_host[n_chunks] == br,
+                "words_bwd_tc: the chunk table must cover the sorted captions [0, br)");
   TcLaunch tl;
   int rc;
   if ((rc = tc_prepare(&tl, "words_bwd_tc", qhat16, q_rows, vhat16, gx, br, bc, t, r, d))) return rc;
-  const int64_t row_bytes = damsm_words_bwd_tc_row_bytes(bc, t, r);
-  const int64_t max_chunk = (workspace_bytes - TC_SCAL_BYTES) / row_bytes;
-  DAMSM_REQUIRE(max_chunk >= 1, "words_bwd_tc: workspace of %lld B is smaller than one caption row (%lld B + %lld B)",
-                (long long)workspace_bytes, (long long)row_bytes, (long long)TC_SCAL_BYTES);
-  // equal chunks (no short tail chunk), even row counts (pairs of caption rows can run as 2-CTA clusters)
-  const int64_t n_chunks = (br + max_chunk - 1) / max_chunk;
-  int64_t chunk = (br + n_chunks - 1) / n_chunks;
-  if ((chunk & 1) && chunk < max_chunk) ++chunk;
+  const int64_t col_bytes = damsm_words_bwd_tc_col_bytes(bc, r);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n_rows = bc * r;
   // Typical magnitudes: dS ~ gamma3/(B T) x [1e-3, 14],  b A ~ gamma3/(B T) x [1e-3, 200].  Scale both by a
@@ -1001,9 +1089,16 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
   uint8_t *ws = reinterpret_cast<uint8_t *>(workspace) + TC_SCAL_BYTES;
   bwd_scalars_kernel<<<1, 1, 0, st>>>(gscale, inv_ds, inv_ba, scal);
   if ((rc = check_launch("words_bwd_tc (scalars)"))) return rc;
-  for (int64_t i0 = 0; i0 < br; i0 += chunk) {
-    const int64_t bi = (br - i0 < chunk) ? (br - i0) : chunk;
-    const int64_t kc = bi * tp;
+  // the word rows of the sorted captions back to back: the K index of the scratch matrices and of the gradient GEMMs
+  tc_pack_q_kernel<<<(unsigned)br, 128, 0, st>>>((const __half *)qhat16, (int)q_rows, (int)d, nw, order, koff, (__half *)qpack16);
+  if ((rc = check_launch("words_bwd_tc (pack q)"))) return rc;
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const int64_t s0 = chunk_pos_host[c], s1 = chunk_pos_host[c + 1];
+    DAMSM_REQUIRE(s1 > s0 && s1 <= br, "words_bwd_tc: bad chunk table entry %lld", (long long)c);
+    const int64_t kbase = koff_host[s0], kc = koff_host[s1] - kbase;
+    DAMSM_REQUIRE(kc > 0 && kc % 16 == 0 && TC_SCAL_BYTES + kc * col_bytes <= workspace_bytes,
+                  "words_bwd_tc: chunk %lld needs %lld B of workspace (have %lld)", (long long)c,
+                  (long long)(TC_SCAL_BYTES + kc * col_bytes), (long long)workspace_bytes);
     __half *x_ds = (__half *)ws;
     __half *x_a = x_ds + n_rows * kc;
     float *svec = reinterpret_cast<float *>(x_a + n_rows * kc);
@@ -1011,38 +1106,34 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
     p.br = (int)br; p.bc = (int)bc; p.T = (int)t; p.R = (int)r; p.D = (int)d;
     p.g1 = gamma1; p.g2 = gamma2; p.g3 = gamma3; p.mask = mask; p.unorm = unorm; p.sim = const_cast<float *>(sim);
     p.stats = const_cast<float *>(stats);
-    p.i0 = (int)i0; p.tp = (int)tp; p.kc = kc; p.row_lse = row_lse; p.col_lse = col_lse; p.gscale = scal;
+    p.nw = nw; p.order = order; p.koff = koff; p.kbase = kbase;
+    p.i0 = (int)s0; p.kc = kc; p.row_lse = row_lse; p.col_lse = col_lse; p.gscale = scal;
     p.labels = labels; p.row_offset = row_offset; p.b_total = b_total; p.kq = kq;
     p.x_ds = x_ds; p.x_a = hmat ? x_a : nullptr; p.svec = svec; p.scale_ds = scale_ds; p.scale_ba = scale_ba;
 #ifdef DAMSM_TC_DEBUG
     p.dbg = getenv("DAMSM_DBG") ? atoi(getenv("DAMSM_DBG")) : 0;
 #endif
-    if ((rc = tc_launch<true>(tl, p, bi, st))) return rc;
+    if ((rc = tc_launch<true>(tl, p, s1 - s0, st))) return rc;
 #ifdef DAMSM_TC_DEBUG
     // development builds only: time the fused recompute kernel alone / stop after it (results are then incomplete)
     if (getenv("DAMSM_BWD_FUSED_ONLY")) continue;
-    if (getenv("DAMSM_DEBUG_SYNC")) {
-      cudaError_t e = cudaStreamSynchronize(st);
-      fprintf(stderr, "damsm debug: fused bwd kernel chunk i0=%lld done: %s\n", (long long)i0, cudaGetErrorString(e));
-      if (getenv("DAMSM_DEBUG_SKIP_GEMM")) continue;
-    }
 #endif
-    const __half *qc = (const __half *)qhat16 + i0 * tp * d;
-    // The two gradient contractions of the chunk on the own tcgen05 GEMM (gemm_tc.cu); the scratch rows, qhat and vhat
-    // are read in place (K-major / MN-major operands); alpha is a device scalar (it carries the upstream-gradient
-    // magnitude, which is only known on the device).
+    // The two gradient contractions of the chunk on the own tcgen05 GEMM (gemm_tc.cu); the scratch rows, the packed
+    // word rows and vhat are read in place (K-major / MN-major operands); alpha is a device scalar (it carries the
+    // upstream-gradient magnitude, which is only known on the device).
     GemmTcArgs g{};
     g.fmt = 0; g.alpha = 1.f; g.alpha_dev = scal + 3; g.allow_split_k = 1;
-    // dvhat (bc*R x D) += X_dS (bc*R x kc) . qhat_chunk (kc x D)
+    const __half *qc = (const __half *)qpack16 + kbase * d;
+    // dvhat (bc*R x D) += X_dS (bc*R x kc) . qpack_chunk (kc x D)
     if (dvhat) {
       g.a = x_ds; g.lda = kc; g.a_mn = 0; g.b = qc; g.ldb = d; g.b_mn = 1;
       g.m = n_rows; g.n = d; g.k = kc; g.accumulate = 1; g.c = dvhat; g.ldc = d;
       if ((rc = launch_gemm_tc(g, st))) return rc;
     }
-    // dqhat_chunk (kc x D) = X_dS^T (kc x bc*R) . vhat (bc*R x D)
-    if (dqhat) {
+    // dqpack_chunk (kc x D) = X_dS^T (kc x bc*R) . vhat (bc*R x D)
+    if (dqpack) {
       g.a = x_ds; g.lda = kc; g.a_mn = 1; g.b = vhat16; g.ldb = d; g.b_mn = 1;
-      g.m = kc; g.n = d; g.k = n_rows; g.accumulate = 0; g.c = dqhat + i0 * tp * d; g.ldc = d;
+      g.m = kc; g.n = d; g.k = n_rows; g.accumulate = 0; g.c = dqpack + kbase * d; g.ldc = d;
       if ((rc = launch_gemm_tc(g, st))) return rc;
     }
     // H_j (R x R) += sum_k s_k A_j[:,k] A_j[:,k]^T: own tcgen05 kernel (hmat_tc.cu), one CTA per image

@@ -141,9 +141,13 @@ class CudaEngine(metaclass=_EngineMeta):
             # per-pair, per-word scalars (rho, ||c||, 1/Y) for the backward: 12*T bytes per pair
             stats = torch.empty((br, bc, 3, t), device=qhat.device, dtype=torch.float32) if want_stats else None
             col["stats"] = stats
+            plan = self.words_plan(mask_u8, t)
+            pad = self.pad_terms_fwd(col["vhat16"], qhat16, unorm, plan["nw"], t, float(gammas[1])) if t > 16 else None
+            col["plan"], col["pad"] = plan, pad
             _lib.call("damsm_words_fwd_tc", qhat16.data_ptr(), qhat16.shape[1], col["vhat16"].data_ptr(),
                       col["gx"].data_ptr(),
-                      unorm.data_ptr(), mask_u8.data_ptr(), br, bc, t, r, d,
+                      unorm.data_ptr(), mask_u8.data_ptr(), plan["nw"].data_ptr(), plan["order"].data_ptr(),
+                      _lib.ptr(pad["epad"]) if pad else None, br, bc, t, r, d,
                       float(gammas[0]), float(gammas[1]), float(gammas[2]), sim.data_ptr(), _lib.ptr(stats),
                       _stream())
         else:
@@ -151,6 +155,36 @@ class CudaEngine(metaclass=_EngineMeta):
                       unorm.data_ptr(), mask_u8.data_ptr(), br, bc, t, r, d,
                       float(gammas[0]), float(gammas[1]), float(gammas[2]), sim.data_ptr(), _stream())
         return sim
+
+    # ---- skip-padded-words plan and closed form (tensor-core path) -----------------------------------------------
+    def words_plan(self, mask_u8, t):
+        """Per-caption word counts ``nw`` (multiples of 16 covering the last unmasked word) and the captions sorted by
+        them, on the device; a pinned host copy of ``nw`` is started for the backward (which sizes its launches by it)."""
+        br = mask_u8.shape[0]
+        dev = mask_u8.device
+        nw = torch.empty(br, device=dev, dtype=torch.int32)
+        order = torch.empty(br, device=dev, dtype=torch.int32)
+        _lib.call("damsm_words_tc_plan", mask_u8.data_ptr(), br, t, nw.data_ptr(), order.data_ptr(), _stream())
+        nw_host = torch.empty(br, dtype=torch.int32, pin_memory=True)
+        nw_host.copy_(nw, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return dict(nw=nw, order=order, nw_host=nw_host, event=ev)
+
+    def pad_terms_fwd(self, vhat16, qhat16, unorm, nw, t, gamma2):
+        """Mean region per image and epad[i][j] = sum over the skipped words of exp(gamma2 rho_bar) (pad_terms.cu)."""
+        bc, r, d = vhat16.shape
+        br, tp, _ = qhat16.shape
+        dev = vhat16.device
+        out = dict(vbar32=torch.empty((bc, d), device=dev, dtype=torch.float32),
+                   vbar16=torch.empty((bc, d), device=dev, dtype=torch.float16),
+                   nbar=torch.empty(bc, device=dev, dtype=torch.float32),
+                   rn=torch.empty(bc, device=dev, dtype=torch.float32),
+                   epad=torch.empty((br, bc), device=dev, dtype=torch.float32))
+        _lib.call("damsm_pad_terms_fwd", vhat16.data_ptr(), qhat16.data_ptr(), unorm.data_ptr(), nw.data_ptr(),
+                  br, bc, t, tp, r, d, float(gamma2), out["vbar32"].data_ptr(), out["vbar16"].data_ptr(),
+                  out["nbar"].data_ptr(), out["rn"].data_ptr(), out["epad"].data_ptr(), _stream())
+        return out
 
     def words_bwd(self, qhat, qhat16, vhat, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
                   row_offset, b_total, gammas, need_dq=True, need_dv=True):
@@ -163,7 +197,7 @@ class CudaEngine(metaclass=_EngineMeta):
         bc, r, _ = gram.shape
         dev = qhat.device
         if self.precision == "bf16":
-            return self._words_bwd_tc(qhat16, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
+            return self._words_bwd_tc(qhat, qhat16, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
                                       row_offset, b_total, gammas, br, bc, t, r, d, need_dq, need_dv)
         dqhat = torch.zeros((br, t, d), device=dev, dtype=torch.float32)
         dvhat = torch.zeros((bc, r, d), device=dev, dtype=torch.float32)
@@ -181,43 +215,98 @@ class CudaEngine(metaclass=_EngineMeta):
     # FIRST call with a given shape (at least 6 GiB, never more than 80 % of what is free), remembered per shape so
     # that the chunking -- and with it the launch geometry -- does not drift from iteration to iteration.
     tc_workspace_bytes = None
-    _tc_ws_rows = {}
+    _tc_ws_cols = {}
 
-    def _tc_workspace(self, dev, br, bc, t, r):
+    def _tc_workspace_cols(self, dev, br, bc, t, r):
+        """Scratch columns (= words of captions) one chunk may hold."""
         lib = _lib.load()
-        row_bytes = lib.damsm_words_bwd_tc_row_bytes(bc, t, r)
+        col_bytes = lib.damsm_words_bwd_tc_col_bytes(bc, r)
         fixed = lib.damsm_words_bwd_tc_fixed_bytes()
         key = (dev.index, br, bc, t, r, self.tc_workspace_bytes)
-        rows = self._tc_ws_rows.get(key)
-        if rows is None:
+        cols = self._tc_ws_cols.get(key)
+        if cols is None:
             budget = self.tc_workspace_bytes
             if budget is None:
                 free = torch.cuda.mem_get_info(dev)[0]
                 budget = min(max(6 << 30, free // 3), int(free * 0.8))
-            rows = int(min(max(1, (budget - fixed) // row_bytes), br))
-            self._tc_ws_rows[key] = rows
-        return fixed + rows * row_bytes, rows
+            cols = int(max(128, (budget - fixed) // col_bytes // 16 * 16))
+            self._tc_ws_cols[key] = cols
+        return cols, col_bytes, fixed
 
-    def _words_bwd_tc(self, qhat16, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
+    @staticmethod
+    def _tc_chunks(nw_sorted, kc_max):
+        """Chunk boundaries (positions in the sorted caption order) with at most kc_max scratch columns per chunk and
+        about equal column counts; koff = prefix sums of the sorted word counts."""
+        import numpy as np
+        koff = np.zeros(len(nw_sorted) + 1, dtype=np.int64)
+        np.cumsum(nw_sorted, out=koff[1:])
+        total = int(koff[-1])
+        n = len(nw_sorted)
+        if n and int(nw_sorted.max()) > kc_max:
+            raise _lib.DamsmError("tensor-core backward: workspace smaller than one caption")
+        n_chunks = max(1, -(-total // kc_max))
+        while True:
+            # boundaries at equal quantiles of the column count; more chunks if one of them does not fit
+            cuts = [int(np.searchsorted(koff, total * c / n_chunks, side="left")) for c in range(1, n_chunks)]
+            pos = sorted(set([0] + [min(max(c, 1), n) for c in cuts] + [n]))
+            sizes = koff[pos[1:]] - koff[pos[:-1]]
+            if sizes.max() <= kc_max or n_chunks >= n:
+                break
+            n_chunks += 1
+        return koff, np.asarray(pos, dtype=np.int64)
+
+    def _words_bwd_tc(self, qhat, qhat16, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,
                       row_offset, b_total, gammas, br, bc, t, r, d, need_dq=True, need_dv=True):
+        import numpy as np
         dev = qhat16.device
         tp = qhat16.shape[1]
-        ws_bytes, ws_rows = self._tc_workspace(dev, br, bc, t, r)
+        plan, pad = col["plan"], col.get("pad")
+        plan["event"].synchronize()                         # the pinned copy of nw (started before the forward kernel)
+        nw_host = plan["nw_host"].numpy()
+        order_host = np.argsort(-nw_host.astype(np.int64), kind="stable").astype(np.int32)
+        kc_max, col_bytes, fixed = self._tc_workspace_cols(dev, br, bc, t, r)
+        koff_host, chunk_pos = self._tc_chunks(nw_host[order_host].astype(np.int64), kc_max)
+        total_k = int(koff_host[-1])
+        kc_need = int((koff_host[chunk_pos[1:]] - koff_host[chunk_pos[:-1]]).max())
+        ws_bytes = fixed + kc_need * col_bytes
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        order = torch.from_numpy(order_host).to(dev)
+        koff = torch.from_numpy(koff_host).to(dev)
+        qpack16 = torch.empty((total_k, d), device=dev, dtype=torch.float16)
+        dqpack = torch.empty((total_k, d), device=dev, dtype=torch.float32) if need_dq else None
         dqhat = torch.empty((br, tp, d), device=dev, dtype=torch.float32) if need_dq else None
         dvhat = torch.zeros((bc, r, d), device=dev, dtype=torch.float32) if need_dv else None
         hmat = torch.zeros((bc, r, r), device=dev, dtype=torch.float32) if need_dv else None
         kq = torch.zeros((br, t), device=dev, dtype=torch.float32)
+        n_chunks = len(chunk_pos) - 1
         _lib.call("damsm_words_bwd_tc", qhat16.data_ptr(), tp, col["vhat16"].data_ptr(), col["gx"].data_ptr(),
-                  unorm.data_ptr(), mask_u8.data_ptr(), sim.data_ptr(), col["stats"].data_ptr(),
+                  unorm.data_ptr(), mask_u8.data_ptr(), plan["nw"].data_ptr(), order.data_ptr(), koff.data_ptr(),
+                  koff_host.ctypes.data, chunk_pos.ctypes.data, n_chunks, sim.data_ptr(), col["stats"].data_ptr(),
                   row_lse.data_ptr(), col_lse.data_ptr(),
                   _lib.ptr(labels), gscale.data_ptr(), int(row_offset), int(b_total), br, bc, t, r, d,
                   float(gammas[0]), float(gammas[1]), float(gammas[2]), ws.data_ptr(), ws_bytes,
-                  _lib.ptr(dqhat), _lib.ptr(dvhat), _lib.ptr(hmat), kq.data_ptr(), _stream())
-        chunks = -(-br // ws_rows)
-        # own kernels: the scalar kernel (counted by the call) + per chunk the fused recompute, the dvhat GEMM and the
+                  qpack16.data_ptr(), _lib.ptr(dqpack), _lib.ptr(dvhat), _lib.ptr(hmat), kq.data_ptr(), _stream())
+        # own kernels: scalars + packing (counted by the call) + per chunk the fused recompute, the dvhat GEMM and the
         # H kernel (image side), the dqhat GEMM (caption side)
-        _lib.add_launches((1 + (2 if need_dv else 0) + (1 if need_dq else 0)) * chunks)
+        _lib.add_launches((1 + (2 if need_dv else 0) + (1 if need_dq else 0)) * n_chunks)
+        # closed form of the skipped words + unpacking of the packed word-row gradients (pad_terms.cu)
+        coef = dqpad = dvbar = scal = None
+        if pad is not None:
+            coef = torch.empty((bc, br * tp), device=dev, dtype=torch.float16)
+            dqpad = torch.empty((br * tp, d), device=dev, dtype=torch.float32) if need_dq else None
+            dvbar = torch.empty((bc, d), device=dev, dtype=torch.float32) if need_dv else None
+            scal = torch.empty(64, device=dev, dtype=torch.float32)
+        g = lambda k: _lib.ptr(pad[k]) if pad is not None else None
+        _lib.call("damsm_pad_terms_bwd", g("vbar32"), g("vbar16"), g("nbar"), g("rn"), qhat16.data_ptr(), qhat.data_ptr(),
+                  unorm.data_ptr(), plan["nw"].data_ptr(), order.data_ptr(), koff.data_ptr(), sim.data_ptr(),
+                  row_lse.data_ptr(), col_lse.data_ptr(), _lib.ptr(labels), gscale.data_ptr(), int(row_offset),
+                  int(b_total), br, bc, t, tp, r, d, float(gammas[1]), float(gammas[2]), _lib.ptr(coef), _lib.ptr(dqpad),
+                  _lib.ptr(dvbar), _lib.ptr(scal), _lib.ptr(dqpack), _lib.ptr(dqhat), kq.data_ptr(), _lib.ptr(dvhat),
+                  _stream())
+        if pad is not None:
+            _lib.add_launches(2 + (2 if need_dq else 0) + (2 if need_dv else 0))
+        elif need_dq:
+            _lib.add_launches(1)
         return (dqhat[:, :t, :] if need_dq else None), dvhat, hmat, kq
 
     # ---- dense contraction on the tensor cores (gemm_tc.cu) ----------------------------------------------------

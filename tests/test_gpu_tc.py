@@ -74,7 +74,8 @@ def test_tc_multi_chunk_backward_matches_exact_path():
     eng = pkg.get_engine("bf16")
     lib = pkg._lib.load()
     old = eng.tc_workspace_bytes
-    eng.tc_workspace_bytes = 20 * lib.damsm_words_bwd_tc_row_bytes(B, T, R)      # 96 rows -> 5 chunks (20,20,20,20,16)
+    # room for 20 full-length captions (80 scratch columns each) per chunk -> several chunks for the 96 captions
+    eng.tc_workspace_bytes = lib.damsm_words_bwd_tc_fixed_bytes() + 20 * 80 * lib.damsm_words_bwd_tc_col_bytes(B, R)
     try:
         res = {}
         for prec in ("fp32", "bf16"):
