@@ -95,6 +95,15 @@ DAMSM_API int damsm_words_bwd_f32(const float *qhat, const float *vhat, const fl
 /* host: dynamic shared memory the fused fp32 pair kernel needs for (T,R); <0 if unsupported */
 DAMSM_API int64_t damsm_words_f32_smem_bytes(int64_t t, int64_t r);
 
+/* Nearest-neighbour resize in front of the CLIP re-encode of the DM-GAN generator loss:
+ *   clip_resized = F.interpolate(fake_imgs[i], size=image_size)        (losses.py:348, default mode 'nearest')
+ * x (planes, hin, win) -> y (planes, hout, wout), contiguous, element size 2 or 4 bytes (a gather: bit-exact);
+ * index map of torch: src = min(floor(dst * (float)in / out), in - 1).  Backward (fp32): dx = scatter-add of dy. */
+DAMSM_API int damsm_resize_nearest_fwd(const void *x, int64_t elem_size, int64_t planes, int64_t hin, int64_t win,
+                                       int64_t hout, int64_t wout, void *y, void *stream);
+DAMSM_API int damsm_resize_nearest_bwd(const float *dy, int64_t planes, int64_t hin, int64_t win, int64_t hout,
+                                       int64_t wout, float *dx, void *stream);
+
 /* Dense contraction on the tensor cores (own persistent tcgen05 kernel, csrc/gemm_tc.cu; no library GEMM):
  *   C (m x n, fp32, pitch ldc)  =|+=  alpha * alpha_dev[0] * A (m x k) . B (k x n)
  * a_mn = 0: A is stored (m, k) row-major with pitch lda;  a_mn = 1: stored (k, m) row-major (i.e. A^T as it lies).

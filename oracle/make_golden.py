@@ -91,12 +91,38 @@ def main_rm(out_dir):
         print(f"{name}: out {e.shape}, kept-mask sum {int(m.sum())}")
 
 
+RPREC_CASES = {"rprec_b9_c100_d64": (0, 9, 100, 64), "rprec_b4_c100_d512": (1, 4, 100, 512), "rprec_b5_c7_d33": (2, 5, 7, 33)}
+
+
+def rprec_inputs(seed, B, C, D):
+    rng = np.random.default_rng(seed)
+    img = rng.standard_normal((B, D)).astype(np.float32)
+    cand = rng.standard_normal((B, C, D)).astype(np.float32)
+    cand[::2, 0] = img[::2] + 0.3 * rng.standard_normal((len(img[::2]), D)).astype(np.float32)
+    return img, cand
+
+
+def main_rprec(out_dir):
+    """R-precision scores (trainer.py:596-601) of the reference's own statements -> tests/golden/aux/."""
+    aux = os.path.join(out_dir, "aux")
+    os.makedirs(aux, exist_ok=True)
+    for name, (seed, B, C, D) in RPREC_CASES.items():
+        img, cand = rprec_inputs(seed, B, C, D)
+        s, h = RS.ref_r_precision(img, cand)
+        np.savez_compressed(os.path.join(aux, name + ".npz"), meta=np.array([seed, B, C, D], np.int64),
+                            scores0=s.astype(np.float32), hit=h)
+        print(f"{name}: hits {int(h.sum())}/{B}")
+
+
 def main():
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "rm_special_token":      # only the token-gather fixtures
         return main_rm(out_dir)
+    if len(sys.argv) > 1 and sys.argv[1] == "r_precision":           # only the R-precision fixtures
+        return main_rprec(out_dir)
     main_rm(out_dir)
+    main_rprec(out_dir)
     for name, (B, T, R, seed, cls, ncls) in CASES.items():
         x = O.make_inputs(B, T, R, seed=seed, class_ids=cls, n_classes=max(ncls, 1))
         w = RS.ref_words_loss(x["words"], x["regions"], x["mask"], x["labels"], x["class_ids"], GAMMAS)

@@ -263,3 +263,39 @@ def ref_step(x, gammas):
         s0, s1 = losses.sent_loss(a, t, lab, cls, B)
         (w0 + w1 + s0 + s1).backward()
     return [float(v.detach()) for v in (w0, w1, s0, s1)]
+
+
+def ref_r_precision(img_code, sent_codes):
+    """Run the reference's own R-precision statements (trainer.py:596-601, inside ``condGANTrainer.sampling``'s
+    per-image loop) on ``img_code`` (B, D) and ``sent_codes`` (B, C, D) (true caption at index 0, as :593 builds it).
+    The method cannot be imported or called (it needs the GAN, the dataset and CLIP), so the five assignments that
+    compute ``scores0`` and the ``torch.argmax(scores0) == 0`` test are cut out of the file with ``ast`` at run time and
+    executed per image -- nothing is copied into this repository.  Returns (scores0 (B, C), hit (B,) bool)."""
+    import ast
+    import numpy as np
+    import torch
+    path = os.path.join(SRC_ROOT, "trainer.py")
+    tree = ast.parse(open(path).read())
+    wanted = ["scores", "img_code_norm", "sent_code_norm", "norm", "scores0"]
+    found, test = {}, None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == "sampling":
+            for sub in ast.walk(node):
+                if isinstance(sub, ast.Assign) and len(sub.targets) == 1 and isinstance(sub.targets[0], ast.Name) \
+                        and sub.targets[0].id in wanted and sub.targets[0].id not in found:
+                    found[sub.targets[0].id] = sub
+                if isinstance(sub, ast.If) and "argmax" in ast.unparse(sub.test) and test is None:
+                    test = sub.test
+    assert set(found) == set(wanted) and test is not None, "trainer.py:596-601 not found"
+    body = [found[k] for k in wanted] + [ast.Assign(targets=[ast.Name(id="_hit", ctx=ast.Store())], value=test, lineno=0)]
+    mod = ast.fix_missing_locations(ast.Module(body=body, type_ignores=[]))
+    code = compile(mod, path, "exec")
+    img = torch.as_tensor(np.asarray(img_code), dtype=torch.float32)
+    cand = torch.as_tensor(np.asarray(sent_codes), dtype=torch.float32)
+    scores, hits = [], []
+    for i in range(img.shape[0]):
+        ns = {"torch": torch, "img_code": img, "sent_code": cand[i], "i": i}
+        exec(code, ns)
+        scores.append(ns["scores0"].reshape(-1).numpy().copy())
+        hits.append(bool(ns["_hit"]))
+    return np.stack(scores), np.asarray(hits)

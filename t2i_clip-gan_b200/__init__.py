@@ -13,11 +13,11 @@ from . import _lib
 from ._lib import DamsmError
 from .engine import CudaEngine, get_engine
 from .patch import patch_reference, unpatch_reference
-from .ops import (DEFAULT_GAMMAS, DamsmFuncAttention, DamsmNTXent, DamsmSentLoss, DamsmWordsLoss, LazyAttnMaps,
+from .ops import (DEFAULT_GAMMAS, clip_resize, generator_regions, DamsmFuncAttention, DamsmNTXent, DamsmSentLoss, DamsmWordsLoss, LazyAttnMaps,
                   combine_column_lse, func_attention, nt_xent, project_regions, r_precision_scores, rm_special_token, sent_loss, standard_ntxent_mask,
                   words_loss)
 
 __all__ = ["words_loss", "sent_loss", "func_attention", "DamsmWordsLoss", "DamsmSentLoss", "DamsmFuncAttention",
            "LazyAttnMaps", "nt_xent", "rm_special_token", "project_regions", "r_precision_scores", "DamsmNTXent", "standard_ntxent_mask", "CudaEngine", "get_engine", "DamsmError", "DEFAULT_GAMMAS", "combine_column_lse",
-           "patch_reference", "unpatch_reference"]
+           "patch_reference", "unpatch_reference", "clip_resize", "generator_regions"]
 __version__ = "0.1.0"

@@ -28,6 +28,8 @@ SIGNATURES = {
     "damsm_words_bwd_f32": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _l, _l, _l, _f, _f, _f,
                             _p, _p, _p, _p, _p],
     "damsm_words_f32_smem_bytes": [_l, _l],
+    "damsm_resize_nearest_fwd": [_p, _l, _l, _l, _l, _l, _l, _p, _p],
+    "damsm_resize_nearest_bwd": [_p, _l, _l, _l, _l, _l, _p, _p],
     "damsm_gemm_tc": [_p, _l, _i, _p, _l, _i, _i, _l, _l, _l, _f, _p, _i, _p, _l, _p],
     "damsm_words_tc_gx_cols": [_l],
     "damsm_gram_pack_tc": [_p, _l, _l, _p, _p],
@@ -64,7 +66,7 @@ _RESTYPE = {"damsm_last_error": C.c_char_p, "damsm_words_f32_smem_bytes": C.c_in
 LAUNCHES = {
     "damsm_l2norm_fwd": 1, "damsm_l2norm_bwd": 1, "damsm_gram_f32": 1, "damsm_gram_bwd_f32": 1,
     "damsm_words_fwd_f32": 1, "damsm_words_bwd_f32": 1,
-    "damsm_gemm_tc": 1, "damsm_gram_pack_tc": 1, "damsm_words_tc_plan": 1, "damsm_words_fwd_tc": 1, "damsm_words_bwd_tc": 2,
+    "damsm_resize_nearest_fwd": 1, "damsm_resize_nearest_bwd": 1, "damsm_gemm_tc": 1, "damsm_gram_pack_tc": 1, "damsm_words_tc_plan": 1, "damsm_words_fwd_tc": 1, "damsm_words_bwd_tc": 2,
     "damsm_pad_terms_fwd": 2, "damsm_ce_stats_f32": 2, "damsm_ce_losses_f32": 1,
     "damsm_cos_logits_f32": 4, "damsm_cos_logits_bwd_f32": 5,
     "damsm_ntxent_fwd_f32": 3, "damsm_ntxent_bwd_f32": 4,

@@ -1,0 +1,71 @@
+// Nearest-neighbour image resize, forward + backward: the glue in front of the CLIP re-encode of the DM-GAN generator
+// loss,  clip_resized = F.interpolate(fake_imgs[i], size=image_size)   (losses.py:348; default mode = 'nearest':
+// 256x256 fakes -> 224x224 CLIP input).  Index map of torch's nearest mode: src = min(floor(dst * (float)in / out), in-1)
+// computed in fp32 -- reproduced literally so that the result is bit-identical (it is a gather).  The backward adds
+// every output gradient to its source pixel (fp32 atomics; when shrinking no two outputs share a source).
+// Memory-bound: algorithmic bytes = read B*C*Hout*Wout sources + write as many (forward).
+#include "common.cuh"
+
+namespace damsm {
+
+template <typename T>
+__global__ void __launch_bounds__(256) resize_nearest_fwd_kernel(const T *__restrict__ x, int64_t planes, int hin, int win,
+                                                                 int hout, int wout, float sh, float sw, T *__restrict__ y) {
+  const int64_t total = planes * hout * wout;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(e % wout);
+    const int oy = (int)((e / wout) % hout);
+    const int64_t pl = e / ((int64_t)wout * hout);
+    const int iy = min((int)floorf(oy * sh), hin - 1), ix = min((int)floorf(ox * sw), win - 1);
+    y[e] = x[(pl * hin + iy) * win + ix];
+  }
+}
+
+__global__ void __launch_bounds__(256) resize_nearest_bwd_kernel(const float *__restrict__ dy, int64_t planes, int hin, int win,
+                                                                 int hout, int wout, float sh, float sw, float *__restrict__ dx) {
+  const int64_t total = planes * hout * wout;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(e % wout);
+    const int oy = (int)((e / wout) % hout);
+    const int64_t pl = e / ((int64_t)wout * hout);
+    const int iy = min((int)floorf(oy * sh), hin - 1), ix = min((int)floorf(ox * sw), win - 1);
+    atomicAdd(dx + (pl * hin + iy) * win + ix, dy[e]);
+  }
+}
+
+}  // namespace damsm
+
+using namespace damsm;
+
+// x (planes, hin, win) -> y (planes, hout, wout), contiguous; elem_size 2 or 4 (raw copies, any 16- or 32-bit type)
+extern "C" int damsm_resize_nearest_fwd(const void *x, int64_t elem_size, int64_t planes, int64_t hin, int64_t win,
+                                        int64_t hout, int64_t wout, void *y, void *stream) {
+  DAMSM_REQUIRE(x && y, "resize_nearest_fwd: null pointer");
+  DAMSM_REQUIRE(elem_size == 2 || elem_size == 4, "resize_nearest_fwd: element size %lld", (long long)elem_size);
+  DAMSM_REQUIRE(hin > 0 && win > 0 && hout > 0 && wout > 0, "resize_nearest_fwd: empty image");
+  const int64_t total = planes * hout * wout;
+  if (total == 0) return 0;
+  const float sh = (float)hin / (float)hout, sw = (float)win / (float)wout;
+  const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  if (elem_size == 4)
+    resize_nearest_fwd_kernel<uint32_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint32_t *)x, planes, (int)hin, (int)win,
+                                                                               (int)hout, (int)wout, sh, sw, (uint32_t *)y);
+  else
+    resize_nearest_fwd_kernel<uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t *)x, planes, (int)hin, (int)win,
+                                                                               (int)hout, (int)wout, sh, sw, (uint16_t *)y);
+  return check_launch("resize_nearest_fwd");
+}
+
+// dy (planes, hout, wout) fp32 -> dx (planes, hin, win) fp32 [OVERWRITTEN]
+extern "C" int damsm_resize_nearest_bwd(const float *dy, int64_t planes, int64_t hin, int64_t win, int64_t hout, int64_t wout,
+                                        float *dx, void *stream) {
+  DAMSM_REQUIRE(dy && dx, "resize_nearest_bwd: null pointer");
+  DAMSM_REQUIRE(hin > 0 && win > 0 && hout > 0 && wout > 0, "resize_nearest_bwd: empty image");
+  DAMSM_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)(planes * hin * win), (cudaStream_t)stream));
+  const int64_t total = planes * hout * wout;
+  if (total == 0) return 0;
+  const float sh = (float)hin / (float)hout, sw = (float)win / (float)wout;
+  const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  resize_nearest_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, planes, (int)hin, (int)win, (int)hout, (int)wout, sh, sw, dx);
+  return check_launch("resize_nearest_bwd");
+}

@@ -442,6 +442,24 @@ class CudaEngine(metaclass=_EngineMeta):
         _lib.add_launches(int(need_dx) + int(need_dw) + int(need_db) - 1)      # two GEMM launches + the column sum
         return dx, dw, db
 
+    # ---- nearest resize in front of the CLIP re-encode (losses.py:348) --------------------------------------------
+    def resize_nearest_fwd(self, x, hout, wout):
+        """x (..., hin, win) contiguous, 2- or 4-byte elements -> (..., hout, wout)."""
+        _require_cuda(x)
+        hin, win = x.shape[-2:]
+        planes = x.numel() // (hin * win) if hin * win else 0
+        y = torch.empty(tuple(x.shape[:-2]) + (hout, wout), device=x.device, dtype=x.dtype)
+        _lib.call("damsm_resize_nearest_fwd", x.data_ptr(), x.element_size(), planes, hin, win, hout, wout, y.data_ptr(),
+                  _stream())
+        return y
+
+    def resize_nearest_bwd(self, dy32, hin, win):
+        hout, wout = dy32.shape[-2:]
+        planes = dy32.numel() // (hout * wout) if hout * wout else 0
+        dx = torch.empty(tuple(dy32.shape[:-2]) + (hin, win), device=dy32.device, dtype=torch.float32)
+        _lib.call("damsm_resize_nearest_bwd", dy32.data_ptr(), planes, hin, win, hout, wout, dx.data_ptr(), _stream())
+        return dx
+
     # ---- rm_special_token (pretrain_DAMSM.py:58-79) ------------------------------------------------------------
     def rm_special_token_fwd(self, x, mask_i64):
         """x (B,n,D) with a contiguous innermost dim, 2- or 4-byte elements; mask_i64 (B,n) int64."""

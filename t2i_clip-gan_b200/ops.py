@@ -408,6 +408,45 @@ def r_precision_scores(img_code, sent_codes, eps=1e-8, *, engine=None):
     return scores, hit.bool()
 
 
+# ----------------------------------------------------------------------------------------------- generator_loss glue
+class DamsmResizeNearest(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, hout, wout, engine):
+        ctx.engine, ctx.in_hw, ctx.dtype = engine, tuple(x.shape[-2:]), x.dtype
+        return engine.resize_nearest_fwd(x.contiguous(), hout, wout)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx = ctx.engine.resize_nearest_bwd(dy.contiguous().float(), *ctx.in_hw)
+        return dx.to(ctx.dtype), None, None, None
+
+
+def clip_resize(images, size, *, engine=None):
+    """Drop-in for ``F.interpolate(fake_imgs[i], size=image_size)`` at losses.py:348 (default mode 'nearest'): the
+    256x256 generator output resized to CLIP's input resolution.  ``images`` (B, C, H, W), ``size`` int or (h, w).
+    One gather kernel forward (bit-identical to torch), one scatter kernel backward."""
+    if images.dim() < 3:
+        raise ValueError("clip_resize: images must be (..., H, W)")
+    hout, wout = (int(size), int(size)) if not isinstance(size, (tuple, list)) else (int(size[0]), int(size[1]))
+    if images.element_size() not in (2, 4) or not images.is_floating_point():
+        raise TypeError(f"clip_resize: unsupported dtype {images.dtype}")
+    eng = engine or get_engine("fp32")
+    return DamsmResizeNearest.apply(images, hout, wout, eng)
+
+
+def generator_regions(region_features, grid=None):
+    """``region_features[:, :, 1:].reshape(-1, D, g, g)`` of losses.py:350 WITHOUT the copy the reshape forces:
+    ``region_features`` is the (B, D, R+1) permuted view ``encode_image_verbose`` returns (model.py:46-48; CLS token
+    first); the result is a strided (B, D, g, g) view that ``words_loss`` reads in place."""
+    if region_features.dim() != 3 or region_features.shape[2] < 2:
+        raise ValueError("generator_regions: expected (B, D, R+1) with the CLS token first")
+    r = region_features.shape[2] - 1
+    g = int(math.isqrt(r)) if grid is None else int(grid)
+    if g * g != r:
+        raise ValueError(f"generator_regions: {r} regions are not a square grid")
+    return region_features[:, :, 1:].unflatten(2, (g, g))
+
+
 # ----------------------------------------------------------------------------------------------- region projection
 class DamsmProjectRegions(torch.autograd.Function):
     """linear_subr + CLS drop (model.py:46,78; pretrain_DAMSM.py:125) with the l2norm prologue of words_loss fused into

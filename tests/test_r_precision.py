@@ -1,6 +1,9 @@
-"""R-precision scoring (trainer.py:587-603): oracle vs the reference's procedure restated with the same
-torch calls (the code lives inside a training method and cannot be imported), CUDA kernel vs oracle."""
+"""R-precision scoring (trainer.py:587-603).  PINNED: the oracle is checked against golden vectors recorded
+from the reference's OWN statements (trainer.py:596-601, cut out of the training method with ``ast`` by
+``oracle/ref_shim.ref_r_precision``; ``oracle/make_golden.py r_precision``), live against them where /root/reference
+exists, and against the procedure port; the CUDA kernel is checked against the oracle."""
 import importlib
+import os
 
 import numpy as np
 import pytest
@@ -16,6 +19,29 @@ def inputs(B, C, D, seed):
     cand = rng.standard_normal((B, C, D)).astype(np.float32)
     cand[::2, 0] = img[::2] + 0.3 * rng.standard_normal((len(img[::2]), D)).astype(np.float32)   # half the images: true caption close
     return img, cand
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aux")
+
+
+@pytest.mark.parametrize("name", ["rprec_b9_c100_d64", "rprec_b4_c100_d512", "rprec_b5_c7_d33"])
+def test_oracle_matches_golden_from_the_reference_statements(name):
+    from oracle import make_golden
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    seed, B, C, D = (int(v) for v in g["meta"])
+    img, cand = make_golden.rprec_inputs(seed, B, C, D)
+    s, h = O.r_precision_scores(img, cand)
+    assert np.abs(s - g["scores0"]).max() < 1e-6 and np.array_equal(h, g["hit"])
+
+
+def test_oracle_matches_live_reference_statements():
+    from oracle import ref_shim
+    if not ref_shim.sources_available():
+        pytest.skip("/root/reference not present")
+    img, cand = inputs(7, 100, 128, 3)
+    s_ref, h_ref = ref_shim.ref_r_precision(img, cand)
+    s, h = O.r_precision_scores(img, cand)
+    assert np.abs(s - s_ref).max() < 1e-6 and np.array_equal(h, h_ref)
 
 
 def test_oracle_matches_procedure_port():
