@@ -60,7 +60,7 @@ def test_c4_full_size_losses_and_gradients_vs_exact_kernel():
 
 def test_c5_regime_row_block_vs_exact_engine():
     """The headline configuration's regime (BASELINE configs[4]: b_total = bc = 4096, T=77, R=196) on a block of 64
-    caption rows: dqhat, dvhat, hmat and kq of the tensor-core backward against the exact fp32 engine with the same
+    caption rows: dqhat, dvhat - H vhat and kq of the tensor-core backward against the exact fp32 engine with the same
     sim / row_lse / col_lse -- the power-of-two fp16 scales of the scratch rows depend on b_total and are exercised
     here at their benchmarked value."""
     BR, BC, T, R = 64, 4096, 77, 196
@@ -89,8 +89,14 @@ def test_c5_regime_row_block_vs_exact_engine():
         gscale = torch.tensor([1.0, 1.0], device="cuda")
         outs[name] = eng.words_bwd(qhat, qhat16, vhat, col, qun, mask_u8, s, row_lse, outs["col_lse"], labels, gscale,
                                    0, BC, GAM)
-    for k, what in enumerate(("dqhat", "dvhat", "hmat", "kq")):
-        e = relmax(outs["bf16"][k], outs["fp32"][k])
+    # dvhat and hmat are compared through what they are for, dvhat - H vhat (ops.DamsmWordsLoss.backward): the
+    # tensor-core path folds the skipped (padded) words' share of H vhat into dvhat instead of into H (pad_terms.cu)
+    res = {}
+    for name, eng in (("fp32", f32), ("bf16", tc)):
+        dq, dv, hm, kq = outs[name]
+        res[name] = (dq, eng.gram_bwd(hm, vhat, dv.clone()), kq)
+    for k, what in enumerate(("dqhat", "dvhat - H vhat", "kq")):
+        e = relmax(res["bf16"][k], res["fp32"][k])
         print(f"C5 regime row block: {what} rel {e:.2e}")
         assert e <= TOL, (what, e)
 
