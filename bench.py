@@ -814,10 +814,8 @@ def measure_roofline(pkg, w, dev, bl, B, rank, group, prec, ms_step):
         words3, regions3 = dev["words"].detach(), dev["regions"].detach()
         qhat, qhat16, qnorm, qunorm = eng.l2norm_fwd(words3, want_bf16=prec == "bf16", pad8=True)
         vhat_l, vhat16_l, vnorm, _ = eng.l2norm_fwd(regions3, want_bf16=prec == "bf16")
-        vhat = pkg.ops._all_gather_rows(vhat_l, group) if prec == "fp32" else vhat_l
         mask_u8 = (dev["mask"] != 0).to(torch.uint8).contiguous()
-        vhat16 = pkg.ops._all_gather_rows(vhat16_l, group) if vhat16_l is not None else None
-        col = eng.pack_columns(pkg.ops._all_gather_rows(eng.gram(vhat_l), group), vhat, vhat16)
+        col, vhat = eng.image_side(vhat_l, vhat16_l, lambda t: pkg.ops._all_gather_rows(t, group))
         sim = eng.words_fwd(qhat, qhat16, vhat, col, qunorm, mask_u8, GAMMAS)
         row_lse, cmax, csum = eng.ce_stats(sim, None, None, rank * bl)
         col_lse = pkg.combine_column_lse(cmax, csum, group)

@@ -112,15 +112,31 @@ class CudaEngine(metaclass=_EngineMeta):
     def pack_columns(self, gram: torch.Tensor, vhat, vhat16=None):
         """Image-side operands of the pair kernels from the (gathered) Gram matrices and normalised regions:
         fp32 path: gram + vhat; tensor-core path: the padded fp16 Gram form with the appended row of ones + vhat16."""
-        col = {"gram": gram}
+        col = {"gram": gram, "shape": tuple(gram.shape[:2])}
         if self.precision == "bf16":
-            bc, r, _ = gram.shape
-            rk = _lib.load().damsm_words_tc_gx_cols(r)
-            gx = torch.empty((bc, r + 1, rk), device=gram.device, dtype=torch.float16)
-            _lib.call("damsm_gram_pack_tc", gram.data_ptr(), bc, r, gx.data_ptr(), _stream())
-            col["gx"] = gx
+            col["gx"] = self._pack_gx(gram)
             col["vhat16"] = vhat16
         return col
+
+    def _pack_gx(self, gram):
+        bc, r, _ = gram.shape
+        rk = _lib.load().damsm_words_tc_gx_cols(r)
+        gx = torch.empty((bc, r + 1, rk), device=gram.device, dtype=torch.float16)
+        _lib.call("damsm_gram_pack_tc", gram.data_ptr(), bc, r, gx.data_ptr(), _stream())
+        return gx
+
+    def image_side(self, vhat_l, vhat16_l, gather):
+        """Image-side operands of the pair kernels for ALL ranks' images from this rank's normalised regions: the Gram
+        matrices are formed (and, tensor-core path, packed to the padded fp16 form with the row of ones) for the LOCAL
+        images only; ``gather`` (all-gather over the ranks, identity on one GPU) then moves exactly what the pair
+        kernels read -- fp16 gx + fp16 vhat (tensor-core path) or fp32 gram + fp32 vhat (exact path)."""
+        gram_l = self.gram(vhat_l)
+        r = gram_l.shape[1]
+        if self.precision == "bf16":
+            gx = gather(self._pack_gx(gram_l))
+            return {"gram": None, "shape": (gx.shape[0], r), "gx": gx, "vhat16": gather(vhat16_l)}, vhat_l
+        gram = gather(gram_l)
+        return {"gram": gram, "shape": (gram.shape[0], r)}, gather(vhat_l)
 
     def words_prepare_columns(self, vhat: torch.Tensor, vhat16=None):
         """Single-GPU convenience: gram + pack_columns."""
@@ -135,7 +151,7 @@ class CudaEngine(metaclass=_EngineMeta):
     def words_fwd(self, qhat, qhat16, vhat, col, unorm, mask_u8, gammas, want_stats=True):
         _require_cuda(qhat, unorm, mask_u8)
         br, t, d = qhat.shape
-        bc, r, _ = col["gram"].shape
+        bc, r = col["shape"]
         sim = torch.empty((br, bc), device=qhat.device, dtype=torch.float32)
         if self.precision == "bf16":
             # per-pair, per-word scalars (rho, ||c||, 1/Y) for the backward: 12*T bytes per pair
@@ -194,7 +210,7 @@ class CudaEngine(metaclass=_EngineMeta):
         None for it (the fp32 path always computes both)."""
         gram = col["gram"]
         br, t, d = qhat.shape
-        bc, r, _ = gram.shape
+        bc, r = col["shape"]
         dev = qhat.device
         if self.precision == "bf16":
             return self._words_bwd_tc(qhat, qhat16, col, unorm, mask_u8, sim, row_lse, col_lse, labels, gscale,

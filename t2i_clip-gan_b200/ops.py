@@ -118,14 +118,17 @@ class DamsmWordsLoss(torch.autograd.Function):
             vhat_l, vhat16_l, vnorm = side[0], (side[1] if engine.precision == "bf16" else None), side[2]
         else:
             vhat_l, vhat16_l, vnorm, _ = engine.l2norm_fwd(regions3, want_bf16=engine.precision == "bf16")
-        # image side: Gram matrices are computed for the local images only and gathered with the operands the
-        # pair kernels read (fp32 path: vhat; tensor-core path: the fp16 copy)
-        gram = _all_gather_rows(engine.gram(vhat_l), group)
-        tc = engine.precision == "bf16"
-        vhat = vhat_l if (group is None or tc) else _all_gather_rows(vhat_l, group)
-        vhat16 = _all_gather_rows(vhat16_l, group) if vhat16_l is not None else None
+        # image side: Gram matrices are computed (and packed) for the local images only; what is gathered is exactly
+        # what the pair kernels read (tensor-core path: fp16 gx + fp16 vhat; exact path: fp32 gram + fp32 vhat)
         cls_all = _all_gather_rows(cls_local, group) if cls_local is not None else None
-        colside = engine.pack_columns(gram, vhat, vhat16)
+        if hasattr(engine, "image_side"):
+            colside, vhat = engine.image_side(vhat_l, vhat16_l, lambda x: _all_gather_rows(x, group))
+        else:                                    # block-level engines without the fused helper (tests/checker_engine.py)
+            gram = _all_gather_rows(engine.gram(vhat_l), group)
+            tc = engine.precision == "bf16"
+            vhat = vhat_l if (group is None or tc) else _all_gather_rows(vhat_l, group)
+            vhat16 = _all_gather_rows(vhat16_l, group) if vhat16_l is not None else None
+            colside = engine.pack_columns(gram, vhat, vhat16)
         sim = engine.words_fwd(qhat, qhat16, vhat, colside, qunorm, mask_u8, gammas)
         row_lse, col_max, col_sum = engine.ce_stats(sim, cls_local, cls_all, row_offset)
         col_lse = combine_column_lse(col_max, col_sum, group)
