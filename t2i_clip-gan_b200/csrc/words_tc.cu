@@ -71,10 +71,12 @@ __host__ __device__ inline TcLayout tc_layout(int NT, int R, int D) {
 // 1 no scratch stores, 2 no sweep 2, 4 no sweeps, 8/16 skip Gx / vhat TMA loads, 32 no softmax math, 64 no MMAs.
 #ifdef DAMSM_TC_DEBUG
 #define DBG(p, bit) ((p).dbg & (bit))
-#define TRACE(p, slot, it, k) do { if ((p).trace && blockIdx.x == 0 && blockIdx.y == 0 && (it) < 16) (p).trace[((slot) * 16 + (it)) * 8 + (k)] = clock64(); } while (0)
+#define TRACE(p, slot, it, k) do { if ((p).trace && blockIdx.x == (p).trace_block && blockIdx.y == 0 && (it) < 16) (p).trace[((slot) * 16 + (it)) * 8 + (k)] = clock64(); } while (0)
+#define TRACEW(p, it, k) do { if ((p).trace && blockIdx.x == (p).trace_block && blockIdx.y == 0 && (it) == 6 && lane == 0) (p).trace[(2 * 16 + warp) * 8 + (k)] = clock64(); } while (0)
 #else
 #define DBG(p, bit) (0)
 #define TRACE(p, slot, it, k) do {} while (0)
+#define TRACEW(p, it, k) do {} while (0)
 #endif
 
 struct TcParams {
@@ -105,6 +107,7 @@ struct TcParams {
   float scale_ds, scale_ba;           // power-of-two scales that keep dS and diag(b)A in fp16's normal range
   long long *trace;                   // development: clock64 trace buffer (debug builds only)
   int dbg;                            // development switches (env DAMSM_DBG): 1 no stores, 2 no sweep 2, 4 no sweeps
+  int trace_block;                    // development: blockIdx.x whose timestamps are recorded
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -302,7 +305,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       int stage = 0, phase = 0;
       auto load = [&](const CUtensorMap *m, int nkb, int j) {
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_spin(&empty[stage], phase ^ 1);
           if (DBG(p, 8) && m == &tmG) { mbar_arrive(&full[stage]); }          // timing experiments only
           else if (DBG(p, 16) && m == &tmV) { mbar_arrive(&full[stage]); }
           else {
@@ -318,8 +321,10 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
       };
-      // same order as the MMA issuer consumes: with two S buffers GEMM1 of the next image precedes GEMM2
-      if (nbuf == 2) {
+      // same order as the MMA issuer consumes.  Forward, two S buffers: GEMM1 of the next image precedes GEMM2 (pass A of
+      // the next pair runs inside the GEMM2 wait and needs S early).  Backward: GEMM2 first -- its Gx blocks are then
+      // already in the ring when e2 is ready, and GEMM1 of the next image hides behind the two sweeps.
+      if (nbuf == 2 && !BWD) {
         if (j0 < j1) load(&tmV, L.nkb_d, j0);
         for (int j = j0; j < j1; ++j) {
           if (j + 1 < j1) load(&tmV, L.nkb_d, j + 1);
@@ -332,7 +337,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else if (warp == MMA_WARP) {
     // ===================================== MMA issuer =====================================
     if (elect_one()) {
-      mbar_wait(q_full, 0);
+      mbar_spin(q_full, 0);
       int stage = 0, phase = 0;
       // The issuing thread is a single lane: its instruction latency, not the tensor pipe, bounded the per-pair time
       // when every MMA rebuilt two 64-bit descriptors.  Keep the constant high words and base low words in registers.
@@ -344,12 +349,12 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const bool two_tiles = L.tiles == 2;
       auto gemm1 = [&](int it) {                       // S^T[buf] = vhat_j qhat_i^T
         const int b = it % nbuf, use = it / nbuf;
-        if (use > 0) mbar_wait(&s_free[b], (use - 1) & 1);
+        if (use > 0) mbar_spin(&s_free[b], (use - 1) & 1);
         tc_fence_after();
         TRACE(p, 0, it, 0);
         const uint32_t d0 = tmem_base + (uint32_t)(b * L.tiles * NT);
         for (int kb = 0; kb < L.nkb_d; ++kb) {
-          mbar_wait(&full[stage], phase);
+          mbar_spin(&full[stage], phase);
           tc_fence_after();
           // descriptors differ only in the 14-bit start-address field (16-byte units): one add per operand
           const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_units, b_lo = q_lo0 + (uint32_t)kb * kb_units;
@@ -369,14 +374,14 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         TRACE(p, 0, it, 1);
       };
       auto gemm2 = [&](int it) {                       // M'^T = Gx_j e2
-        mbar_wait(e2_ready, it & 1);
-        if (it > 0) mbar_wait(m_free, (it - 1) & 1);
+        mbar_spin(e2_ready, it & 1);
+        if (it > 0) mbar_spin(m_free, (it - 1) & 1);
         tc_fence_after();
         TRACE(p, 0, it, 2);
         int left = L.k2_steps;
         const uint32_t dm = tmem_base + col_m;
         for (int kb = 0; kb < L.nkb_r; ++kb) {
-          mbar_wait(&full[stage], phase);
+          mbar_spin(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_units, b_lo = e_lo0 + (uint32_t)kb * kb_units;
           const int nk = min(4, left);
@@ -399,7 +404,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         TRACE(p, 0, it, 3);
       };
       const int n = j1 - j0;
-      if (nbuf == 2) {
+      if (nbuf == 2 && !BWD) {
         if (n > 0) gemm1(0);
         for (int it = 0; it < n; ++it) {
           if (it + 1 < n) gemm1(it + 1);
@@ -529,7 +534,10 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const char *nx = reinterpret_cast<const char *>(p.stats + ((int64_t)i * p.bc + j + 1) * 3 * T) + lane * 128;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
         }
+        if (warp == 1 && lane == 0) TRACE(p, 1, it, 0);
+        TRACEW(p, it, 0);
         pass_a(it);                                                 // backward: e1 stays live only until pass B
+        TRACEW(p, it, 1);
       }
       const int b = it % nbuf;
       const uint32_t t_s = t_lane + (uint32_t)(b * L.tiles * NT);
@@ -1030,6 +1038,7 @@ extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void
   p.nw = nw; p.order = order; p.epad = epad;
 #ifdef DAMSM_TC_DEBUG
   p.dbg = getenv("DAMSM_DBG") ? atoi(getenv("DAMSM_DBG")) : 0;
+  p.trace_block = getenv("DAMSM_TRACE_BLOCK") ? atoi(getenv("DAMSM_TRACE_BLOCK")) : 0;
   if (getenv("DAMSM_TRACE")) {
     static long long *tr = nullptr;
     if (!tr) cudaMalloc(&tr, 3 * 16 * 8 * sizeof(long long));
@@ -1113,8 +1122,32 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
 #ifdef DAMSM_TC_DEBUG
     p.dbg = getenv("DAMSM_DBG") ? atoi(getenv("DAMSM_DBG")) : 0;
 #endif
+#ifdef DAMSM_TC_DEBUG
+    static long long *trb = nullptr;
+    if (getenv("DAMSM_TRACE_BWD")) {
+      if (!trb) cudaMalloc(&trb, 3 * 16 * 8 * sizeof(long long));
+      cudaMemsetAsync(trb, 0, 3 * 16 * 8 * sizeof(long long), st);
+      p.trace = trb;
+      p.trace_block = getenv("DAMSM_TRACE_BLOCK") ? atoi(getenv("DAMSM_TRACE_BLOCK")) : 0;
+      if (p.trace_block >= s1 - s0) p.trace_block = (int)(s1 - s0 - 1);
+    }
+#endif
     if ((rc = tc_launch<true>(tl, p, s1 - s0, st))) return rc;
 #ifdef DAMSM_TC_DEBUG
+    if (getenv("DAMSM_TRACE_BWD")) {     // tools/trace_bwd.py: per-pair clock trace of one CTA
+      long long h[3 * 16 * 8];
+      cudaMemcpy(h, trb, sizeof(h), cudaMemcpyDeviceToHost);
+      long long t0 = h[(1 * 16 + 0) * 8 + 0];
+      fprintf(stderr, "bwd trace chunk %lld block %d (cycles since the first pass A):\n", (long long)c, p.trace_block);
+      for (int w = 0; w < 16; ++w)
+        fprintf(stderr, "warp %2d it6: top %7lld passA %7lld e2arrive %7lld m_full %7lld sweeps_end %7lld\n", w,
+                h[(2 * 16 + w) * 8 + 0] - t0, h[(2 * 16 + w) * 8 + 1] - t0, h[(2 * 16 + w) * 8 + 2] - t0, h[(2 * 16 + w) * 8 + 4] - t0,
+                h[(2 * 16 + w) * 8 + 5] - t0);
+      for (int it = 0; it < 12; ++it)
+        fprintf(stderr, "it %2d MMA: g1start %7lld g1issued %7lld g2start %7lld g2issued %7lld | SM: top %7lld passA %7lld B1+coef %7lld m_full %7lld sweeps %7lld\n", it,
+                h[(0 * 16 + it) * 8 + 0] - t0, h[(0 * 16 + it) * 8 + 1] - t0, h[(0 * 16 + it) * 8 + 2] - t0, h[(0 * 16 + it) * 8 + 3] - t0,
+                h[(1 * 16 + it) * 8 + 0] - t0, h[(1 * 16 + it) * 8 + 1] - t0, h[(1 * 16 + it) * 8 + 2] - t0, h[(1 * 16 + it) * 8 + 3] - t0, h[(1 * 16 + it) * 8 + 4] - t0);
+    }
     // development builds only: time the fused recompute kernel alone / stop after it (results are then incomplete)
     if (getenv("DAMSM_BWD_FUSED_ONLY")) continue;
 #endif
