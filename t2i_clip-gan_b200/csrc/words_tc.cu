@@ -128,6 +128,13 @@ __device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {   // sa
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// Packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2, sm_100): two independent IEEE fp32 operations per issued instruction.
+// The softmax / sweep passes are bound by the instruction issue rate of 14 warps, and they naturally work on pairs of
+// adjacent word columns.
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 unpack_half2(uint32_t v) {
   return __half22float2(*reinterpret_cast<const __half2 *>(&v));
 }
@@ -246,8 +253,8 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float *tb = vu + NT;                                        // 0 for real words, -inf for padding and t >= T
   float *tb2 = tb + NT;                                       // 0 for t < T, -inf for t >= T
   float *viy = tb2 + NT, *vY = viy + 2 * NT;                  // 1/Y [2][NT] (backward), Y [3][NT] (forward)
-  float4 *vc = reinterpret_cast<float4 *>(vY + 3 * NT);       // [2][NT] backward coefficients
-  float *red1 = reinterpret_cast<float *>(vc + 2 * NT), *red2 = red1 + 24 * NT;   // [3][NT][8] each
+  float *vc = vY + 3 * NT;                                    // backward coefficients [2][4][NT]: sp*cx, -sp*cy, cz, 1/Y
+  float *red1 = vc + 8 * NT, *red2 = red1 + 24 * NT;          // [3][NT][8] each
   float *zbuf = red2 + 24 * NT, *wbuf = zbuf + 1024;          // [2 parities][2 halves][256] each
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -278,7 +285,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     vu[t] = in ? p.unorm[(int64_t)i * T + t] : 1.f;
     tb[t] = (in && p.mask[(int64_t)i * T + t]) ? 0.f : -INFINITY;
     tb2[t] = in ? 0.f : -INFINITY;
-    vc[t] = vc[NT + t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < 8; ++k) vc[k * NT + t] = 0.f;
     viy[t] = viy[NT + t] = 0.f;
     for (int k = 0; k < 24; ++k) red1[t * 24 + k] = red2[t * 24 + k] = 0.f;   // [3][NT][8]: unused warp slots stay 0
   }
@@ -500,7 +507,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t ts_ = t_lane + (uint32_t)(b_ * L.tiles * NT);
       mbar_wait(&s_full[b_], (it_ / nbuf) & 1);
       tc_fence_after();
-      float zp = 0.f;
+      float2 zp2 = make_float2(0.f, 0.f);
       if (DBG(p, 32)) {
 #pragma unroll
         for (int c = 0; c < NH; ++c) e1[c] = 1.f;
@@ -513,14 +520,16 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float4 ba = tb4[2 * c], bb = tb4[2 * c + 1];
         const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float e = ex2f(fmaf(x[k], kLog2e, bias[k]));
-          e1[c * 8 + k] = e;
-          zp += e;
+        for (int k = 0; k < 8; k += 2) {
+          const float2 a = f2fma(make_float2(x[k], x[k + 1]), f2(kLog2e), make_float2(bias[k], bias[k + 1]));
+          const float2 e = make_float2(ex2f(a.x), ex2f(a.y));
+          e1[c * 8 + k] = e.x;
+          e1[c * 8 + k + 1] = e.y;
+          zp2 = f2add(zp2, e);
         }
       }
       float *zb = zbuf + (it_ & 1) * 512;
-      zb[half * 256 + widx] = zp;
+      zb[half * 256 + widx] = zp2.x + zp2.y;
       // only the two warps that share these rows (word halves) exchange Z: a 64-thread named barrier per pair
       named_bar_sync(2 + (warp & 7), 64);
       invZ = 1.f / (zb[widx] + zb[256 + widx]);
@@ -546,8 +555,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int rb3 = it % 3;                                       // the forward tail runs one pair late: 3 buffers
       float *red1w = red1w0 + rb3 * NT * 8, *red2w = red2w0 + rb3 * NT * 8;
       float *vYb = vY + rb3 * NT;
-      float4 *vcb = vc + rb * NT;
-      float *viyb = viy + rb * NT;
+      float *vcb = vc + rb * 4 * NT;
       float *wb = wbuf + rb * 512;
       if (DBG(p, 32)) {
 #pragma unroll
@@ -561,10 +569,8 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int tl = 0; tl < NH; tl += 2) {
         if (DBG(p, 32)) break;
         if (tl >= nh) break;
-        const float2 bz = tb22[tl >> 1];
-        const float a0 = ex2f(fmaf(e1[tl], k2, bz.x));
-        const float a1 = ex2f(fmaf(e1[tl + 1], k2, bz.y));
-        const uint32_t h2 = pack_half2(a0, a1) & rowmask;          // rows >= R contribute nothing
+        const float2 ar = f2fma(make_float2(e1[tl], e1[tl + 1]), f2(k2), tb22[tl >> 1]);
+        const uint32_t h2 = pack_half2(ex2f(ar.x), ex2f(ar.y)) & rowmask;   // rows >= R contribute nothing
         e2p[tl >> 1] = h2;
         if (k_row) {
           sts_u16(e2a[tl & 7] + tl * 128, h2 & 0xffffu);
@@ -579,9 +585,9 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld<W>(t_s + cbeg, x);
 #pragma unroll
         for (int k = 0; k < W; k += 2) {
-          const float2 f = unpack_half2(e2p[(cbeg + k) >> 1]);     // the values the tensor core sees
-          x[k] *= f.x;
-          x[k + 1] *= f.y;
+          const float2 pr = f2mul(make_float2(x[k], x[k + 1]), unpack_half2(e2p[(cbeg + k) >> 1]));   // e2 as the tensor core sees it
+          x[k] = pr.x;
+          x[k + 1] = pr.y;
         }
         const float cs = warp_colsum<W>(x, lane);
         if (lane < W) red1w[(cbeg + lane) * 8] = cs;
@@ -589,16 +595,18 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // backward: the sweeps only need P = e1/Z to fp16 accuracy; halving its registers keeps them spill-free
       // (spills go to L2 here: the L1 is almost entirely carved out as shared memory)
       uint32_t e1h[BWD ? NH / 2 : 1];
-      if constexpr (BWD) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      TRACEW(p, it, 2);
+      if (lane == 0) mbar_arrive(e2_ready);
+      if constexpr (BWD) {                                          // behind the arrival: GEMM2 does not need it
 #pragma unroll
         for (int k = 0; k < NH / 2; ++k) {
           if (2 * k >= nh) break;
-          e1h[k] = pack_half2(e1[2 * k] * invZ, e1[2 * k + 1] * invZ);
+          const float2 pq = f2mul(make_float2(e1[2 * k], e1[2 * k + 1]), f2(invZ));
+          e1h[k] = pack_half2(pq.x, pq.y);
         }
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(e2_ready);
       if constexpr (!BWD) {
         if (!DBG(p, 32)) {
           DAMSM_TC_COLUMN_BLOCKS(pass_b2);
@@ -633,9 +641,11 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               const float beta = g * p.g3 * omega;                  // dL/drho_t
               const float a = beta / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
               const float bq = (n > kCosEps) ? beta * rho / (n * n) : 0.f;
-              vcb[t] = make_float4(p.g1 * a * iy, p.g1 * bq * iy * iy, a * iy * p.scale_ds, 0.f);
+              vcb[t] = p.scale_ds * p.g1 * a * iy;                  // sp * cx
+              vcb[NT + t] = -p.scale_ds * p.g1 * bq * iy * iy;      // -sp * cy
+              vcb[2 * NT + t] = a * iy * p.scale_ds;                // cz
+              vcb[3 * NT + t] = iy;
               svp[t] = bq * p.scale_ba;
-              viyb[t] = iy;
               atomicAdd(p.kq + (int64_t)i * T + t, beta * rho * bw_gm);
             } else if (t < NTi) {
               svp[t] = 0.f;
@@ -668,9 +678,9 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
 #pragma unroll
           for (int k = 0; k < W; k += 2) {
-            const float2 f = unpack_half2(e2p[(cbeg + k) >> 1]);
-            x[k] *= f.x;
-            x[k + 1] *= f.y;
+            const float2 pr = f2mul(make_float2(x[k], x[k + 1]), unpack_half2(e2p[(cbeg + k) >> 1]));
+            x[k] = pr.x;
+            x[k + 1] = pr.y;
           }
           const float cs = warp_colsum<W>(x, lane);
           if (lane < W) red2w[(cbeg + lane) * 8] = cs;
@@ -686,11 +696,13 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         if (warp == 1 && lane == 0) TRACE(p, 1, it, 4);
       } else {
-        const float4 *vch = vcb + c0;
-        const float *viyh = viyb + c0;
+        // per-word coefficients (staged by warp 0, pre-scaled by the fp16 scale sp): sp*cx, -sp*cy, cz, 1/Y
+        const float *cxh = vcb + c0, *cyh = cxh + NT, *czh = cyh + NT, *iyh = czh + NT;
+        TRACEW(p, it, 4);
         if (!DBG(p, 4)) {
-        // ---- W = sum_t P dP with dP = gamma1 A (a S - b M)  (this row, all words: two halves via wbuf) ----
-        float wp = 0.f;
+        // ---- sp W = sum_t P (sp dP) with dP = gamma1 A (a S - b M') = f (cx S - cy M')  (this row, all words: two halves
+        //      via wbuf); packed fp32x2 arithmetic on pairs of adjacent words ----
+        float2 wp2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < NH / 8; ++c) {
           if (c * 8 >= nh) break;
@@ -703,21 +715,20 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int tl = c * 8 + k;
             const float2 f = unpack_half2(e2p[tl >> 1]);
             const float2 pp = unpack_half2(e1h[tl >> 1]);          // P
-            const float4 ca = vch[tl], cb = vch[tl + 1];
-            wp = fmaf(pp.x, f.x * (ca.x * xs[k] - ca.y * xm[k]), wp);
-            wp = fmaf(pp.y, f.y * (cb.x * xs[k + 1] - cb.y * xm[k + 1]), wp);
+            const float2 cx = *reinterpret_cast<const float2 *>(cxh + tl), cy = *reinterpret_cast<const float2 *>(cyh + tl);
+            const float2 d = f2fma(cy, make_float2(xm[k], xm[k + 1]), f2mul(cx, make_float2(xs[k], xs[k + 1])));
+            wp2 = f2fma(pp, f2mul(f, d), wp2);
           }
         }
-        wb[half * 256 + widx] = wp;
+        wb[half * 256 + widx] = wp2.x + wp2.y;
         named_bar_sync(2 + (warp & 7), 64);
-        const float Wr = wb[widx] + wb[256 + widx];
-        // ---- dS = a A + P (dP - W); A; diag(b) A  -> scaled fp16 rows of the scratch matrices ----
+        const float2 nW = f2(-(wb[widx] + wb[256 + widx]));          // -sp W
+        // ---- sp dS = cz f + P (sp dP - sp W); A = f / Y  -> fp16 rows of the scratch matrices ----
         if (!DBG(p, 2)) {
           const int64_t row = (int64_t)j * R + (valid ? rg : 0);
           const int64_t off = row * p.kc + (p.koff[spos] - p.kbase) + c0;
           uint4 *o_ds = reinterpret_cast<uint4 *>(p.x_ds + off);
           uint4 *o_a = reinterpret_cast<uint4 *>(p.x_a + off);
-          const float sp = p.scale_ds;
 #pragma unroll
           for (int c = 0; c < NH / 8; ++c) {
             if (c * 8 < nh) {                                        // CTA-uniform: tcgen05.ld is warp-collective
@@ -731,13 +742,13 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const int tl = c * 8 + k;
                 const float2 f = unpack_half2(e2p[tl >> 1]);
                 const float2 pp = unpack_half2(e1h[tl >> 1]);
-                const float4 ca = vch[tl], cb = vch[tl + 1];
-                const float dp0 = f.x * (ca.x * xs[k] - ca.y * xm[k]);
-                const float dp1 = f.y * (cb.x * xs[k + 1] - cb.y * xm[k + 1]);
-                const float ds0 = fmaf(ca.z, f.x, sp * pp.x * (dp0 - Wr));
-                const float ds1 = fmaf(cb.z, f.y, sp * pp.y * (dp1 - Wr));
-                pk_ds[k >> 1] = pack_half2_sat(ds0, ds1);
-                pk_a[k >> 1] = pack_half2(viyh[tl] * f.x, viyh[tl + 1] * f.y);
+                const float2 cx = *reinterpret_cast<const float2 *>(cxh + tl), cy = *reinterpret_cast<const float2 *>(cyh + tl);
+                const float2 cz = *reinterpret_cast<const float2 *>(czh + tl), iy = *reinterpret_cast<const float2 *>(iyh + tl);
+                const float2 d = f2fma(cy, make_float2(xm[k], xm[k + 1]), f2mul(cx, make_float2(xs[k], xs[k + 1])));
+                const float2 ds = f2fma(pp, f2fma(f, d, nW), f2mul(cz, f));
+                const float2 av = f2mul(iy, f);
+                pk_ds[k >> 1] = pack_half2_sat(ds.x, ds.y);
+                pk_a[k >> 1] = pack_half2(av.x, av.y);
               }
               if (valid && !DBG(p, 1)) {
                 // streaming stores: the scratch is written once and read back by the GEMMs much later
@@ -748,6 +759,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
         }
+        TRACEW(p, it, 5);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
