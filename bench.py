@@ -743,9 +743,11 @@ def main():
     # ---- N > 1: sharded vs unsharded losses and gradients on a small side case (kept in the SCALE record) ---------
     shard_parity = measure_shard_parity(pkg, world, rank, group, prec) if world > 1 else None
 
-    cpu_base = None
+    cpu_base = eager_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = time_cpu_reference(w, 5)[0]
+        if B <= 64:                  # the small configurations are also compared with eager PyTorch on this GPU
+            eager_gpu = time_eager_gpu_reference(w, ms_step)
 
     if rank == 0:
         scored = B * B / (ms_step * 1e-3)
@@ -758,11 +760,39 @@ def main():
                     algorithmic_tflops=algorithmic_flops(B, T, R) / (ms_step * 1e-3) / 1e12,
                     losses=loss_vals, wall_ms_per_step=t_wall / args.steps * 1e3,
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu_base,
-                    shard_parity=shard_parity)
+                    eager_gpu_baseline=eager_gpu, shard_parity=shard_parity)
         emit(json.dumps(line))
     if group is not None:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def time_eager_gpu_reference(w, ours_ms):
+    """The unmodified reference (oracle/_ref byte code or /root/reference) run eagerly on this GPU, same inputs, full
+    size: a reported baseline like cpu_baseline (the reference is sync-bound on a GPU: ~54 host syncs per caption)."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        return None
+    try:
+        x = make_inputs(w, torch.float32)
+        xin = {k: (v.numpy() if torch.is_tensor(v) else v) for k, v in x.items()}
+        xin["labels"] = np.arange(w["B"])
+        step = ref_shim.ref_step_gpu(xin, GAMMAS)
+        for _ in range(2):
+            losses = step()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            step()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        ms = float(np.median(ts)) * 1e3
+        return dict(kind="reference (unmodified losses.py), eager PyTorch on the same GPU", ms_per_step=ms,
+                    value=w["B"] / (ms * 1e-3), unit="caption-image pairs/s", speedup_of_this_repo=ms / ours_ms,
+                    losses=[float(v) for v in losses.cpu()])
+    except Exception as e:                                          # a baseline must never break the measurement
+        return dict(kind="reference on the same GPU", error=repr(e)[:200])
 
 
 def measure_shard_parity(pkg, world, rank, group, prec):

@@ -265,6 +265,34 @@ def ref_step(x, gammas):
     return [float(v.detach()) for v in (w0, w1, s0, s1)]
 
 
+def ref_step_gpu(x, gammas, device="cuda"):
+    """The same pass as ``ref_step`` with the UNMODIFIED reference running eagerly on the GPU (its own cfg.CUDA path,
+    no patches): the "same-GPU eager PyTorch" baseline of SURVEY 8(d) for the small configurations.  Returns a closure
+    that runs one forward + backward (inputs already on the device) and returns the four losses as a tensor."""
+    import numpy as np
+    import torch
+    losses, _, cfg = load()
+    cfg.CUDA = True
+    cfg.TRAIN.SMOOTH.GAMMA3 = float(gammas[2])
+    t = {k: torch.tensor(np.asarray(x[k]), dtype=torch.float32, device=device).requires_grad_(True)
+         for k in ("words", "regions", "img", "sent")}
+    B = t["words"].shape[0]
+    m = torch.tensor(np.asarray(x["mask"]), dtype=torch.int64)            # arrives on the CPU (pretrain_DAMSM.py:110)
+    lab = torch.tensor(np.asarray(x["labels"]), dtype=torch.int64, device=device)
+    cl = torch.tensor(np.asarray(x["cap_len"]), dtype=torch.int64)
+    cls = None if x.get("class_ids") is None else np.asarray(x["class_ids"])
+
+    def step():
+        for v in t.values():
+            v.grad = None
+        w0, w1, _ = losses.words_loss(t["regions"].permute(0, 2, 1), t["words"].permute(0, 2, 1), lab, cl, cls, B, m,
+                                      float(gammas[0]), float(gammas[1]), float(gammas[2]))
+        s0, s1 = losses.sent_loss(t["img"], t["sent"], lab, cls, B)
+        (w0 + w1 + s0 + s1).backward()
+        return torch.stack([w0.detach(), w1.detach(), s0.detach(), s1.detach()])
+    return step
+
+
 def ref_r_precision(img_code, sent_codes):
     """Run the reference's own R-precision statements (trainer.py:596-601, inside ``condGANTrainer.sampling``'s
     per-image loop) on ``img_code`` (B, D) and ``sent_codes`` (B, C, D) (true caption at index 0, as :593 builds it).
