@@ -55,9 +55,9 @@ def emit(line):
 
 GAMMAS = (4.0, 5.0, 10.0)
 D = 512
-# DRAM bytes per scored pair of the word-loss launches (forward 2.8 KB + fused backward 71.6 KB written/read once;
-# the gradient GEMMs and the H kernel re-read the scratch: + 3 x 31.4 KB), profiles/r1_ncu_tc_summary.md
-TRAFFIC_BYTES_PER_PAIR = 2.8e3 + 71.6e3 + 3 * 31.4e3
+# DRAM bytes per scored pair of the word-loss launches (ncu --set full at B=592, U[T/3,T] caption lengths: forward 3.5 KB,
+# fused backward 56.5 KB, the two gradient GEMMs 49.4 KB, the H kernel 23.8 KB), profiles/r2_ncu_summary.md section 3
+TRAFFIC_BYTES_PER_PAIR = 3.5e3 + 56.5e3 + 49.4e3 + 23.8e3
 # BASELINE.json configs[0..4]
 WORKLOADS = {
     "c1": dict(B=48, T=18, R=49, cls=True, precision="fp32", seed=2026, desc="CUB bird DAMSM shape"),
@@ -873,12 +873,12 @@ def measure_roofline(pkg, w, dev, bl, B, rank, group, prec, ms_step):
     ach = f_step / (ms_step * 1e-3) / 1e12
     sustained = peaks.get("bf16_sustained")
     # DRAM traffic of the word-loss launches per scored pair from the committed ncu --set full captures
-    # (profiles/r2_ncu_summary.md); the capture is at B=256, the per-pair figure is scaled by this step's pairs
+    # (profiles/r2_ncu_summary.md); the capture is at B=592, the per-pair figure is scaled by this step's pairs
     traffic = TRAFFIC_BYTES_PER_PAIR * bl * B if (prec == "bf16" and TRAFFIC_BYTES_PER_PAIR) else None
     return dict(bound="tensor", achieved=ach, peak=peaks["bf16"], unit="TFLOP/s", frac=ach / peaks["bf16"],
                 peak_sustained=sustained, frac_of_sustained=(ach / sustained if sustained else None),
                 traffic=traffic,
-                traffic_note=("from capture: ncu dram__bytes_read+write per scored pair of the word-loss launches at B=256 "
+                traffic_note=("from capture: ncu dram__bytes_read+write per scored pair of the word-loss launches at B=592 "
                               "x this step's pairs (not measured in this run)"),
                 peak_source=peaks["src"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
                 kernel=("whole step (words_loss + sent_loss fwd+bwd); dominant launches: words_tc_kernel<FWD>, "
