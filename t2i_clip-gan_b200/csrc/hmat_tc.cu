@@ -13,7 +13,8 @@
 namespace damsm {
 using namespace tc;
 
-constexpr int HM_THREADS = 320;   // warps 0-7: scale + epilogue, 8: TMA producer, 9: MMA issuer
+constexpr int HM_SCALE_WARPS = 16; // warps 0-15 form the scaled copy (0-7 also run the epilogue), 16: TMA producer, 17: MMA issuer
+constexpr int HM_THREADS = (HM_SCALE_WARPS + 2) * 32;
 constexpr int HM_SA = 5;          // TMA stages of A (the ring must cover ~2.5k cycles of TMA + commit latency)
 constexpr int HM_SB = 2;          // scaled-copy buffers
 
@@ -47,28 +48,28 @@ __global__ void __launch_bounds__(HM_THREADS, 1) hmat_tc_kernel(const __grid_con
     *reinterpret_cast<uint4 *>(smem + o) = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < HM_SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < HM_SB; ++s) { mbar_init(&b_full[s], 8); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < HM_SB; ++s) { mbar_init(&b_full[s], HM_SCALE_WARPS); mbar_init(&b_empty[s], 1); }
     mbar_init(d_full, 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<512>(tmem_ptr);
-  if (warp == 8 && lane == 0) prefetch_tmap(&tmA);
+  if (warp == HM_SCALE_WARPS + 1) tmem_alloc<512>(tmem_ptr);
+  if (warp == HM_SCALE_WARPS && lane == 0) prefetch_tmap(&tmA);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 8) {
+  if (warp == HM_SCALE_WARPS) {
     if (elect_one()) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % HM_SA;
-        mbar_wait(&a_empty[s], ((kb / HM_SA) & 1) ^ 1);
+        mbar_spin(&a_empty[s], ((kb / HM_SA) & 1) ^ 1);
         mbar_arrive_expect_tx(&a_full[s], stage_bytes);
         tma_load_3d(sa + s * stage_bytes, &tmA, &a_full[s], kb * 64, 0, j);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == HM_SCALE_WARPS + 1) {
     if (elect_one()) {
       const uint64_t dproto = umma_desc_k_sw128(0);
       const uint32_t desc_hi = (uint32_t)(dproto >> 32), dlo = (uint32_t)dproto;
@@ -77,8 +78,8 @@ __global__ void __launch_bounds__(HM_THREADS, 1) hmat_tc_kernel(const __grid_con
       const uint32_t idesc = umma_idesc_f16(p.n16);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % HM_SA, u = kb % HM_SB;
-        mbar_wait(&a_full[s], (kb / HM_SA) & 1);
-        mbar_wait(&b_full[u], (kb / HM_SB) & 1);
+        mbar_spin(&a_full[s], (kb / HM_SA) & 1);
+        mbar_spin(&b_full[u], (kb / HM_SB) & 1);
         tc_fence_after();
         const int64_t left = p.kc - (int64_t)kb * 64;
         const int nk = left >= 64 ? 4 : (int)((left + 15) / 16);
@@ -114,20 +115,32 @@ __global__ void __launch_bounds__(HM_THREADS, 1) hmat_tc_kernel(const __grid_con
         v = fminf(fmaxf(v, -65504.f), 65504.f);
         ss[u * 64 + threadIdx.x] = __float2half_rn(v);
       }
-      named_bar_sync(1, 256);
+      named_bar_sync(1, HM_SCALE_WARPS * 32);
       mbar_wait(&a_full[s], (kb / HM_SA) & 1);
       const uint8_t *src = sa + s * stage_bytes;
       uint8_t *dst = sb + u * stage_bytes;
       const uint4 *sc = reinterpret_cast<const uint4 *>(ss + u * 64);
-      for (int c = threadIdx.x; c < nchunk; c += 256) {
-        const int row = c >> 3, pc = c & 7, lc = pc ^ (row & 7);  // physical / logical 16-byte chunk of the row
-        uint4 v = *reinterpret_cast<const uint4 *>(src + c * 16);
-        const uint4 w = sc[lc];
-        __half2 *vh = reinterpret_cast<__half2 *>(&v);
-        const __half2 *wh = reinterpret_cast<const __half2 *>(&w);
+      // a thread's chunks are HM_SCALE_WARPS*32 apart: a multiple of 8, so every one of them is the same logical
+      // 16-byte chunk of its row up to the row's swizzle; all loads of a batch are issued before the first use
+      constexpr int STEP = HM_SCALE_WARPS * 32;
+      for (int c0 = threadIdx.x; c0 < nchunk; c0 += 4 * STEP) {
+        uint4 v[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) vh[q] = __hmul2(vh[q], wh[q]);
-        *reinterpret_cast<uint4 *>(dst + c * 16) = v;
+        for (int q = 0; q < 4; ++q)
+          if (c0 + q * STEP < nchunk) v[q] = *reinterpret_cast<const uint4 *>(src + (c0 + q * STEP) * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = c0 + q * STEP;
+          if (c < nchunk) {
+            const int row = c >> 3, lc = (c & 7) ^ (row & 7);       // logical 16-byte chunk of the row
+            const uint4 w = sc[lc];
+            __half2 *vh = reinterpret_cast<__half2 *>(&v[q]);
+            const __half2 *wh = reinterpret_cast<const __half2 *>(&w);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) vh[e] = __hmul2(vh[e], wh[e]);
+            *reinterpret_cast<uint4 *>(dst + c * 16) = v[q];
+          }
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -139,7 +152,7 @@ __global__ void __launch_bounds__(HM_THREADS, 1) hmat_tc_kernel(const __grid_con
     const int tile = warp >> 2;
     const int r = tile * 128 + (warp & 3) * 32 + lane;
     const float alpha = *p.alpha;
-    if (tile < p.tiles) {
+    if (warp < 8 && tile < p.tiles) {
       const uint32_t t0 = tmem_base + (((uint32_t)(warp & 3) * 32) << 16) + tile * p.n16;
       float *hrow = p.hmat + ((int64_t)j * p.R + (r < p.R ? r : 0)) * p.R;
       for (int c0 = 0; c0 < p.n16; c0 += 16) {                     // warp-uniform trip count: tcgen05.ld is collective
@@ -155,7 +168,7 @@ __global__ void __launch_bounds__(HM_THREADS, 1) hmat_tc_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem_base);
+  if (warp == HM_SCALE_WARPS + 1) tmem_dealloc<512>(tmem_base);
 }
 
 int make_map_f16(CUtensorMap *m, const void *base, uint64_t n0, uint64_t n1, uint64_t n2, uint64_t pitch1_elems,
