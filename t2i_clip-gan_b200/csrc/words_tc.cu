@@ -102,9 +102,11 @@ struct TcParams {
   const int64_t *labels;
   int64_t row_offset, b_total;
   float *kq;
-  __half *x_ds, *x_a;                 // scratch matrices [(j, r)][(i_local, t)], fp16: scaled dS, and A
-  float *svec;                        // (bc, kc): scale_ba * b_t per (image, caption, word), for the H kernel
-  float scale_ds, scale_ba;           // power-of-two scales that keep dS and diag(b)A in fp16's normal range
+  __half *x_ds;                       // scratch matrix [(j, r)][(i_local, t)], fp16: scaled dS
+  int store_e;                        // the un-normalised softmax-2 numerators e2 leave the chip as the second scratch matrix
+                                      // [(i_local, t)][(j, r)] (fp16, word-major): one TMA store of the GEMM2 operand per pair
+  float *svec;                        // (bc, kc): scale_e * b_t / Y_t^2 per (image, caption, word), for the H kernel
+  float scale_ds, scale_e;            // power-of-two scales that keep dS and b e2 / Y^2 in fp16's normal range
   long long *trace;                   // development: clock64 trace buffer (debug builds only)
   int dbg;                            // development switches (env DAMSM_DBG): 1 no stores, 2 no sweep 2, 4 no sweeps
   int trace_block;                    // development: blockIdx.x whose timestamps are recorded
@@ -228,7 +230,7 @@ template <int NT, bool BWD, int NW, int CL>
 __global__ void __launch_bounds__(NW * 32, 1)
 words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
                 const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmV2,
-                const __grid_constant__ CUtensorMap tmG2, TcParams p) {
+                const __grid_constant__ CUtensorMap tmG2, const __grid_constant__ CUtensorMap tmE, TcParams p) {
   constexpr int NH = NT / 2;                 // words per softmax thread
   constexpr int TC_THREADS = NW * 32;
   constexpr int TMA_WARP = (NW == 16) ? 7 : 16;
@@ -247,13 +249,14 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t *s_free = q_full + 3;                      // 9,10
   uint64_t *e2_ready = q_full + 5, *m_full = q_full + 6, *m_free = q_full + 7;   // 11,12,13
   uint64_t *red_full = q_full + 8;                                               // 14 (forward: reductions published)
-  uint64_t *coef_full = q_full + 9;                                              // 15 (backward: coefficients published)
+  uint64_t *coef_full = q_full + 8;                                              // 14,15 (backward: coefficients of even / odd pairs published)
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 16);
+  uint64_t *e2_free = bars + 17;                                                 // backward: the e2 operand has left the chip
   float *vu = reinterpret_cast<float *>(misc + 256);          // [NT] ||qhat_t||
   float *tb = vu + NT;                                        // 0 for real words, -inf for padding and t >= T
   float *tb2 = tb + NT;                                       // 0 for t < T, -inf for t >= T
   float *viy = tb2 + NT, *vY = viy + 2 * NT;                  // 1/Y [2][NT] (backward), Y [3][NT] (forward)
-  float *vc = vY + 3 * NT;                                    // backward coefficients [2][4][NT]: sp*cx, -sp*cy, cz, 1/Y
+  float *vc = vY + 3 * NT;                                    // backward coefficients [2][4][NT]: sp*cx, -sp*cy, cz, (unused)
   float *red1 = vc + 8 * NT, *red2 = red1 + 24 * NT;          // [3][NT][8] each
   float *zbuf = red2 + 24 * NT, *wbuf = zbuf + 1024;          // [2 parities][2 halves][256] each
 
@@ -276,8 +279,9 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // the softmax warps arrive once per warp (lane 0 after __syncwarp): 448 per-thread arrivals on one shared-memory
     // word serialise and were the longest item of the per-pair critical path
     mbar_init(&s_free[0], L.act_warps); mbar_init(&s_free[1], L.act_warps);
-    mbar_init(e2_ready, L.act_warps); mbar_init(m_free, L.act_warps); mbar_init(red_full, L.act_warps);
-    mbar_init(coef_full, 1);
+    mbar_init(e2_ready, L.act_warps); mbar_init(m_free, L.act_warps);
+    if constexpr (BWD) { mbar_init(&coef_full[0], L.act_warps); mbar_init(&coef_full[1], L.act_warps); mbar_init(e2_free, 1); }
+    else mbar_init(red_full, L.act_warps);
     fence_barrier_init();
   }
   for (int t = threadIdx.x; t < NT; t += TC_THREADS) {
@@ -288,6 +292,14 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int k = 0; k < 8; ++k) vc[k * NT + t] = 0.f;
     viy[t] = viy[NT + t] = 0.f;
     for (int k = 0; k < 24; ++k) red1[t * 24 + k] = red2[t * 24 + k] = 0.f;   // [3][NT][8]: unused warp slots stay 0
+  }
+  if (BWD && threadIdx.x == 32) {
+    float *bwc0 = reinterpret_cast<float *>(misc + 160);
+    int64_t *bwl0 = reinterpret_cast<int64_t *>(misc + 176);
+    const int64_t gi = p.row_offset + i;
+    const float ib = 1.f / (float)p.b_total;
+    bwc0[0] = p.row_lse[i]; bwc0[1] = p.gscale[0] * ib; bwc0[2] = p.gscale[1] * ib; bwc0[3] = p.gscale[2];
+    bwl0[0] = p.labels ? p.labels[gi] : gi; bwl0[1] = gi;
   }
   if (warp == MMA_WARP) tmem_alloc<512>(tmem_ptr);
   if (warp == TMA_WARP && lane == 0) {
@@ -410,6 +422,20 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_commit(m_full);
         TRACE(p, 0, it, 3);
       };
+      // backward: the fp16 e2 operand of GEMM2 (words x regions, exactly what the tensor core multiplied) IS the second
+      // scratch matrix: once GEMM2 has read it, 16-word boxes go from shared memory to x_e[(caption, word)][(image, region)]
+      // by TMA -- no register-path stores, no instructions in the softmax warps.  The H kernel folds 1/Y^2 into its
+      // per-word scale (A = e2 / Y).
+      auto estore = [&](int it) {
+        mbar_spin(m_full, it & 1);                                   // GEMM2 of this pair has consumed the operand
+        const int krow = (int)(p.koff[spos] - p.kbase);
+        for (int kb = 0; kb < L.nkb_r; ++kb)
+          for (int m = 0; m < NTi; m += 16)
+            tma_store_3d(&tmE, E2 + kb * NT * 128 + m * 128, kb * 64, j0 + it, krow + m);
+        bulk_commit_group();
+        bulk_wait_group_read0();                                     // shared memory has been read: B1 may overwrite it
+        mbar_arrive(e2_free);
+      };
       const int n = j1 - j0;
       if (nbuf == 2 && !BWD) {
         if (n > 0) gemm1(0);
@@ -418,7 +444,12 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           gemm2(it);
         }
       } else {
-        for (int it = 0; it < n; ++it) { gemm1(it); gemm2(it); }
+        for (int it = 0; it < n; ++it) {
+          gemm1(it);
+          if (BWD && p.store_e && it > 0) estore(it - 1);
+          gemm2(it);
+        }
+        if (BWD && p.store_e && n > 0) { estore(n - 1); bulk_wait_group0(); }
       }
     }
   } else if (warp < 16 && (warp & 7) < L.act_warps / 2) {
@@ -445,19 +476,13 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float *red1w0 = red1 + c0 * 8 + (warp & 7), *red2w0 = red2 + c0 * 8 + (warp & 7);
     const int widx = (warp & 7) * 32 + lane;                        // row slot in zbuf / wbuf
     constexpr int CPL = (NT + 31) / 32;                             // words per lane in the one-warp sections
-    // backward, warp 0: per-row constants of dL/dsim (both cross-entropies, losses.py:265-269)
-    float bw_rl = 0.f, bw_g0 = 0.f, bw_g1 = 0.f, bw_ib = 0.f, bw_gm = 0.f;
-    int64_t bw_gi = 0, bw_li = 0;
-    if (BWD && warp == 0) {
-      bw_gi = p.row_offset + i;
-      bw_li = p.labels ? p.labels[bw_gi] : bw_gi;
-      bw_rl = p.row_lse[i];
-      // the upstream gradients enter normalised by their larger magnitude, which is folded back into the GEMM / H
-      // epilogue scale and into kq: the fp16 range of the scratch rows then does not depend on the loss weight
-      // (LAMBDA = 50 in clip_coco_DMGAN.yml, an AMP loss scale of 2^16, ...)
-      bw_g0 = p.gscale[0]; bw_g1 = p.gscale[1]; bw_gm = p.gscale[2];
-      bw_ib = 1.f / (float)p.b_total;
-    }
+    // backward: per-row constants of dL/dsim (both cross-entropies, losses.py:265-269), kept in shared memory (every
+    // softmax warp reads them once per pair in bwd_coef; registers are the scarce resource of this kernel).
+    // The upstream gradients enter normalised by their larger magnitude, which is folded back into the GEMM / H
+    // epilogue scale and into kq: the fp16 range of the scratch rows then does not depend on the loss weight
+    // (LAMBDA = 50 in clip_coco_DMGAN.yml, an AMP loss scale of 2^16, ...)
+    float *bwc = reinterpret_cast<float *>(misc + 160);             // [0] row_lse, [1] g0/B, [2] g1/B, [3] |g| max
+    int64_t *bwl = reinterpret_cast<int64_t *>(misc + 176);         // [0] label of this row, [1] global row index
     // ---- serial tail of the forward, one warp: per-word cosine (losses.py:197-198), gamma2 log-sum-exp (:199-203),
     //      statistics for the backward.  It runs one pair late, while GEMM2 of the next pair is in flight (every warp
     //      idles there), so it is off the critical path; the bookkeeping it reads is double-buffered by pair parity.
@@ -535,12 +560,60 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       invZ = 1.f / (zb[widx] + zb[256 + widx]);
       k2 = p.g1 * kLog2e * invZ;
     };
+    // ---- backward: per-word coefficients of pair `it_` from the statistics the forward saved (rho, ||c||, 1/Y):
+    //      beta = dL/drho, a = beta/(n u), b = beta rho / n^2.  Runs ONE PAIR AHEAD, inside the GEMM2 wait of pair it_-1
+    //      (prologue for the first pair), and is SPREAD over the softmax warps (a few words per warp, one lane per word):
+    //      done by warp 0 alone for the current pair, its chain of dependent global loads was what every warp waited for
+    //      after GEMM2, and one pair ahead it still made warp 0 the slowest warp of every pair.  Two barriers /
+    //      coefficient buffers by pair parity; a buffer is rewritten only after every warp has left the sweeps of pair
+    //      it_-2 (m_free).
+    const int cwarp = (warp & 7) + (warp >> 3) * (L.act_warps / 2);          // 0 .. act_warps-1
+    const int cwords = (NT + L.act_warps - 1) / L.act_warps;                  // words per warp (<= 32)
+    auto bwd_coef = [&](int it_, int j_) {
+      float *vcb_ = vc + (it_ & 1) * 4 * NT;
+      const int64_t pair = (int64_t)i * p.bc + j_;
+      const float *st = p.stats + pair * 3 * T;
+      const int t = cwarp * cwords + lane;
+      const bool mine = lane < cwords && t < NTi;
+      const bool in = mine && t < T;
+      const float rho = in ? st[t] : 0.f;                                     // independent loads first
+      const float n = in ? st[T + t] : 1.f;
+      const float iy = in ? st[2 * T + t] : 0.f;
+      const float sv = p.sim[pair];
+      const float cl = p.col_lse[j_];
+      const int64_t lj = p.labels ? p.labels[j_] : (int64_t)j_;
+      float g = 0.f;
+      if (sv != -INFINITY) {                                                  // exactly 0 where class-masked
+        const float gr = __expf(sv - bwc[0]) - (bwl[0] == j_ ? 1.f : 0.f);
+        const float gc = __expf(sv - cl) - (lj == bwl[1] ? 1.f : 0.f);
+        g = bwc[1] * gr + bwc[2] * gc;
+      }
+      const float lse = (sv != -INFINITY) ? sv * (p.g2 / p.g3) : 0.f;       // sim = gamma3/gamma2 * lse
+      if (it_ >= 2) mbar_wait(m_free, (it_ - 2) & 1);                        // the sweeps of pair it_-2 read this buffer
+      float bq = 0.f;
+      if (in) {
+        const float omega = __expf(p.g2 * rho - lse);
+        const float beta = g * p.g3 * omega;                                  // dL/drho_t
+        const float a = beta / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
+        bq = (n > kCosEps) ? beta * rho / (n * n) : 0.f;
+        vcb_[t] = p.scale_ds * p.g1 * a * iy;                                 // sp * cx
+        vcb_[NT + t] = -p.scale_ds * p.g1 * bq * iy * iy;                     // -sp * cy
+        vcb_[2 * NT + t] = a * iy * p.scale_ds;                               // cz
+        atomicAdd(p.kq + (int64_t)i * T + t, beta * rho * bwc[3]);
+      }
+      if (mine) p.svec[(int64_t)j_ * p.kc + (p.koff[spos] - p.kbase) + t] = bq * iy * iy * p.scale_e;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&coef_full[it_ & 1]);
+    };
+    if constexpr (BWD) {
+      if (j0 < j1) bwd_coef(0, j0);
+    }
     if (!BWD && j0 < j1) pass_a(0);
     for (int j = j0, it = 0; j < j1; ++j, ++it) {
       if constexpr (BWD) {
         // the per-pair statistics are streamed from HBM exactly once: start fetching the next pair's lines now
-        if (warp == 0 && j + 1 < j1 && lane < 8) {
-          const char *nx = reinterpret_cast<const char *>(p.stats + ((int64_t)i * p.bc + j + 1) * 3 * T) + lane * 128;
+        if (warp == 0 && j + 2 < j1 && lane < 8) {
+          const char *nx = reinterpret_cast<const char *>(p.stats + ((int64_t)i * p.bc + j + 2) * 3 * T) + lane * 128;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
         }
         if (warp == 1 && lane == 0) TRACE(p, 1, it, 0);
@@ -565,6 +638,9 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // ---- pass B: e2 = exp(gamma1 P) (softmax over regions, un-normalised) -> fp16 B operand of GEMM2;
       //      forward also forms the N' = sum_r e2 S partial sums ----
       // B1 (critical path): e2 for every owned word -> fp16 -> the B operand of GEMM2, then GEMM2 can start.
+      if constexpr (BWD) {
+        if (p.store_e && it > 0) mbar_wait(e2_free, (it - 1) & 1);  // the previous pair's e2 has been stored
+      }
 #pragma unroll
       for (int tl = 0; tl < NH; tl += 2) {
         if (DBG(p, 32)) break;
@@ -616,45 +692,8 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (lane == 0) mbar_arrive(&s_free[b]);                     // forward: S is dead from here on
       }
       if constexpr (BWD) {
-        // ---- warp 0: per-word coefficients from the statistics the forward saved (rho, ||c||, 1/Y):
-        //      beta = dL/drho, a = beta/(n u), b = beta rho / n^2.  Runs while GEMM2 is in flight; the sweeps of every
-        //      warp read it after m_full, which GEMM2 signals only after this warp... (published by coef_full).
-        if (warp == 0) {
-          const int64_t pair = (int64_t)i * p.bc + j;
-          const float sv = p.sim[pair];
-          float g = 0.f;
-          if (sv != -INFINITY) {                                    // exactly 0 where class-masked
-            const int64_t lj = p.labels ? p.labels[j] : (int64_t)j;
-            const float gr = __expf(sv - bw_rl) - (bw_li == j ? 1.f : 0.f);
-            const float gc = __expf(sv - p.col_lse[j]) - (lj == bw_gi ? 1.f : 0.f);
-            g = (bw_g0 * gr + bw_g1 * gc) * bw_ib;
-          }
-          const float lse = (sv != -INFINITY) ? sv * (p.g2 / p.g3) : 0.f;   // sim = gamma3/gamma2 * lse
-          const float *st = p.stats + pair * 3 * T;
-          float *svp = p.svec + (int64_t)j * p.kc + (p.koff[spos] - p.kbase);
-#pragma unroll
-          for (int q = 0; q < CPL; ++q) {
-            const int t = q * 32 + lane;
-            if (t < T && t < NTi) {
-              const float rho = st[t], n = st[T + t], iy = st[2 * T + t];
-              const float omega = __expf(p.g2 * rho - lse);
-              const float beta = g * p.g3 * omega;                  // dL/drho_t
-              const float a = beta / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
-              const float bq = (n > kCosEps) ? beta * rho / (n * n) : 0.f;
-              vcb[t] = p.scale_ds * p.g1 * a * iy;                  // sp * cx
-              vcb[NT + t] = -p.scale_ds * p.g1 * bq * iy * iy;      // -sp * cy
-              vcb[2 * NT + t] = a * iy * p.scale_ds;                // cz
-              vcb[3 * NT + t] = iy;
-              svp[t] = bq * p.scale_ba;
-              atomicAdd(p.kq + (int64_t)i * T + t, beta * rho * bw_gm);
-            } else if (t < NTi) {
-              svp[t] = 0.f;
-            }
-          }
-        }
-      }
-      if constexpr (BWD) {
-        if (warp == 0) { __syncwarp(); if (lane == 0) mbar_arrive(coef_full); }
+        // coefficients of the NEXT pair while GEMM2 of this one is in flight (see bwd_coef)
+        if (j + 1 < j1) bwd_coef(it + 1, j + 1);
       }
       if (warp == 1 && lane == 0) TRACE(p, 1, it, 2);
       if constexpr (!BWD) {
@@ -662,7 +701,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (warp == 0 && it > 0) fwd_tail(it - 1, j - 1);
       }
       mbar_wait(m_full, it & 1);
-      if constexpr (BWD) mbar_wait(coef_full, it & 1);
+      if constexpr (BWD) mbar_wait(&coef_full[it & 1], (it >> 1) & 1);
       if (warp == 1 && lane == 0) TRACE(p, 1, it, 3);
       tc_fence_after();
       if constexpr (!BWD) {
@@ -697,7 +736,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (warp == 1 && lane == 0) TRACE(p, 1, it, 4);
       } else {
         // per-word coefficients (staged by warp 0, pre-scaled by the fp16 scale sp): sp*cx, -sp*cy, cz, 1/Y
-        const float *cxh = vcb + c0, *cyh = cxh + NT, *czh = cyh + NT, *iyh = czh + NT;
+        const float *cxh = vcb + c0, *cyh = cxh + NT, *czh = cyh + NT;
         TRACEW(p, it, 4);
         if (!DBG(p, 4)) {
         // ---- sp W = sum_t P (sp dP) with dP = gamma1 A (a S - b M') = f (cx S - cy M')  (this row, all words: two halves
@@ -728,7 +767,6 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const int64_t row = (int64_t)j * R + (valid ? rg : 0);
           const int64_t off = row * p.kc + (p.koff[spos] - p.kbase) + c0;
           uint4 *o_ds = reinterpret_cast<uint4 *>(p.x_ds + off);
-          uint4 *o_a = reinterpret_cast<uint4 *>(p.x_a + off);
 #pragma unroll
           for (int c = 0; c < NH / 8; ++c) {
             if (c * 8 < nh) {                                        // CTA-uniform: tcgen05.ld is warp-collective
@@ -736,24 +774,21 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               tmem_ld8_issue(t_s + c * 8, xs);
               tmem_ld8_issue(t_m + c * 8, xm);
               tmem_wait16(xs, xm);
-              uint32_t pk_ds[4], pk_a[4];
+              uint32_t pk_ds[4];
 #pragma unroll
               for (int k = 0; k < 8; k += 2) {
                 const int tl = c * 8 + k;
                 const float2 f = unpack_half2(e2p[tl >> 1]);
                 const float2 pp = unpack_half2(e1h[tl >> 1]);
                 const float2 cx = *reinterpret_cast<const float2 *>(cxh + tl), cy = *reinterpret_cast<const float2 *>(cyh + tl);
-                const float2 cz = *reinterpret_cast<const float2 *>(czh + tl), iy = *reinterpret_cast<const float2 *>(iyh + tl);
+                const float2 cz = *reinterpret_cast<const float2 *>(czh + tl);
                 const float2 d = f2fma(cy, make_float2(xm[k], xm[k + 1]), f2mul(cx, make_float2(xs[k], xs[k + 1])));
                 const float2 ds = f2fma(pp, f2fma(f, d, nW), f2mul(cz, f));
-                const float2 av = f2mul(iy, f);
                 pk_ds[k >> 1] = pack_half2_sat(ds.x, ds.y);
-                pk_a[k >> 1] = pack_half2(av.x, av.y);
               }
               if (valid && !DBG(p, 1)) {
                 // streaming stores: the scratch is written once and read back by the GEMMs much later
                 __stcs(o_ds + c, make_uint4(pk_ds[0], pk_ds[1], pk_ds[2], pk_ds[3]));
-                if (p.x_a) __stcs(o_a + c, make_uint4(pk_a[0], pk_a[1], pk_a[2], pk_a[3]));
               }
             }
           }
@@ -812,6 +847,23 @@ int make_map_f16(CUtensorMap *m, const void *base, uint64_t n0, uint64_t n1, uin
   return 0;
 }
 
+// fp16 tensor (n2, n1, n0) with explicit box (b2, b1, b0 = 64), 128-byte swizzle
+int make_map_f16_box(CUtensorMap *m, const void *base, uint64_t n0, uint64_t n1, uint64_t n2, uint64_t pitch1_elems,
+                     uint64_t pitch2_elems, uint32_t box1, uint32_t box2) {
+  PFN_encodeTiled enc = get_encode();
+  DAMSM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {n0, n1, n2};
+  cuuint64_t strides[2] = {pitch1_elems * 2, pitch2_elems * 2};
+  cuuint32_t box[3] = {64, box1, box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DAMSM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) dims=(%llu,%llu,%llu) box=(64,%u,%u)", (int)r,
+                (unsigned long long)n0, (unsigned long long)n1, (unsigned long long)n2, box1, box2);
+  return 0;
+}
+
 static int pick_nt(int T) {
   if (T <= 32) return 32;
   if (T <= 64) return 64;
@@ -837,6 +889,7 @@ struct TcLaunch {
   int nt;
   TcLayout L;
   CUtensorMap tmQ, tmV, tmG, tmV2, tmG2, tmVh, tmGh;   // full-row boxes; cluster mode: second / first half-row boxes
+  CUtensorMap tmE;                                     // backward: store map of the e2 scratch of the current chunk
   int sms;
   bool cluster_ok;
 };
@@ -861,7 +914,7 @@ static int tc_prepare(TcLaunch *tl, const char *who, const void *qhat16, int64_t
   if ((rc = make_map_f16(&tl->tmV, vhat16, d, r, bc, d, r * d, tl->L.rs))) return rc;
   if ((rc = make_map_f16(&tl->tmG, gx, rk, r + 1, bc, rk, (r + 1) * rk, tl->L.rs))) return rc;
   // cluster mode (pairs of captions share the image stream): half-row boxes for the two CTAs of a cluster
-  tl->tmV2 = tl->tmV; tl->tmG2 = tl->tmG;
+  tl->tmV2 = tl->tmV; tl->tmG2 = tl->tmG; tl->tmE = tl->tmQ;
   tl->cluster_ok = tl->nt == 80 && tl->L.act_warps <= 14 && tl->L.rs - tl->L.rs_half >= 8 && !getenv("DAMSM_TC_NO_CLUSTER");
   if (tl->cluster_ok) {
     CUtensorMap a, b;
@@ -904,11 +957,11 @@ static int tc_launch(const TcLaunch &tl, TcParams &p, int64_t rows, cudaStream_t
     if (tl.L.act_warps <= 14) {                                                                                       \
       DAMSM_CUDA(cudaFuncSetAttribute(words_tc_kernel<NT_, BWD, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)tl.L.total));                                                              \
-      words_tc_kernel<NT_, BWD, 16, 1><<<grid, 16 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, tl.tmV, tl.tmG, p); \
+      words_tc_kernel<NT_, BWD, 16, 1><<<grid, 16 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, tl.tmV, tl.tmG, tl.tmE, p); \
     } else {                                                                                                          \
       DAMSM_CUDA(cudaFuncSetAttribute(words_tc_kernel<NT_, BWD, 18, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)tl.L.total));                                                              \
-      words_tc_kernel<NT_, BWD, 18, 1><<<grid, 18 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, tl.tmV, tl.tmG, p); \
+      words_tc_kernel<NT_, BWD, 18, 1><<<grid, 18 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, tl.tmV, tl.tmG, tl.tmE, p); \
     }                                                                                                                 \
   } while (0)
   // forward: always when possible; backward: opt-in (DAMSM_TC_CLUSTER_BWD=1) -- its kernel is bound by the softmax
@@ -923,7 +976,7 @@ static int tc_launch(const TcLaunch &tl, TcParams &p, int64_t rows, cudaStream_t
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    DAMSM_CUDA(cudaLaunchKernelEx(&cfg, kern, tl.tmQ, tl.tmVh, tl.tmGh, tl.tmV2, tl.tmG2, p));
+    DAMSM_CUDA(cudaLaunchKernelEx(&cfg, kern, tl.tmQ, tl.tmVh, tl.tmGh, tl.tmV2, tl.tmG2, tl.tmE, p));
     return check_launch(BWD ? "words_bwd_tc (fused recompute, 2-CTA clusters)" : "words_fwd_tc (2-CTA clusters)");
   }
   switch (tl.nt) {
@@ -936,8 +989,8 @@ static int tc_launch(const TcLaunch &tl, TcParams &p, int64_t rows, cudaStream_t
   return check_launch(BWD ? "words_bwd_tc (fused recompute)" : "words_fwd_tc");
 }
 
-int launch_hmat_tc(const void *x_a, const float *svec, int64_t bc, int64_t r, int64_t kc, const float *alpha_dev,
-                   float *hmat, cudaStream_t st);   // hmat_tc.cu
+int launch_hmat_tc(const void *x_e, int64_t rp, const float *svec, int64_t bc, int64_t r, int64_t kc,
+                   const float *alpha_dev, float *hmat, cudaStream_t st);   // hmat_tc.cu
 
 // Device scalars of one backward call (head of the workspace): normalised upstream gradients, their magnitude, and
 // the epilogue scales that undo the fp16 scaling of the scratch rows.
@@ -1074,9 +1127,10 @@ extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void
 
 extern "C" int64_t damsm_words_bwd_tc_fixed_bytes(void) { return TC_SCAL_BYTES; }
 
-// bytes of scratch per K column (= one word of one caption of a chunk): two fp16 matrices [(j,r)] + the per-word scales
-// (bc) fp32
-extern "C" int64_t damsm_words_bwd_tc_col_bytes(int64_t bc, int64_t r) { return 2 * bc * r * 2 + bc * 4; }
+// bytes of scratch per K column (= one word of one caption of a chunk): the fp16 dS matrix [(j,r)][k], the fp16 e2 matrix
+// [k][(j, r padded to a multiple of 8)] and the per-word scales (bc) fp32
+static inline int64_t tc_e_pitch(int64_t r) { return (r + 7) / 8 * 8; }
+extern "C" int64_t damsm_words_bwd_tc_col_bytes(int64_t bc, int64_t r) { return bc * r * 2 + bc * tc_e_pitch(r) * 2 + bc * 4; }
 
 extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
                                   const float *unorm, const uint8_t *mask, const int32_t *nw, const int32_t *order,
@@ -1104,8 +1158,11 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
   // power of two so that they sit in the middle of fp16's normal range [6e-5, 65504] (stores saturate), and undo
   // the scale in the GEMM epilogue (alpha).
   const float lb = rintf(log2f((float)b_total * (float)t / fmaxf(gamma3, 1e-3f)));
-  const float scale_ds = exp2f(lb + 6.f), scale_ba = exp2f(lb + 4.f);
-  const float inv_ds = 1.f / scale_ds, inv_ba = 1.f / scale_ba;
+  // e2 in [1, e^gamma1], 1/Y in [1/(R e^gamma1), 1/R]: b e2 / Y^2 = (b A) / Y is centred like b A was by the extra factor
+  // R e^(gamma1/2)
+  const float le = rintf(log2f((float)r) + 0.5f * gamma1 * kLog2e);
+  const float scale_ds = exp2f(lb + 6.f), scale_e = exp2f(lb + 4.f + le);
+  const float inv_ds = 1.f / scale_ds, inv_ba = 1.f / scale_e;
   float *scal = reinterpret_cast<float *>(workspace);
   uint8_t *ws = reinterpret_cast<uint8_t *>(workspace) + TC_SCAL_BYTES;
   bwd_scalars_kernel<<<1, 1, 0, st>>>(gscale, inv_ds, inv_ba, scal);
@@ -1121,8 +1178,9 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
                   "words_bwd_tc: chunk %lld needs %lld B of workspace (have %lld)", (long long)c,
                   (long long)(TC_SCAL_BYTES + kc * col_bytes), (long long)workspace_bytes);
     __half *x_ds = (__half *)ws;
-    __half *x_a = x_ds + n_rows * kc;
-    float *svec = reinterpret_cast<float *>(x_a + n_rows * kc);
+    const int64_t rp = tc_e_pitch(r);
+    __half *x_e = x_ds + n_rows * kc;                               // [kc][bc * rp]
+    float *svec = reinterpret_cast<float *>(x_e + kc * bc * rp);
     TcParams p{};
     p.br = (int)br; p.bc = (int)bc; p.T = (int)t; p.R = (int)r; p.D = (int)d;
     p.g1 = gamma1; p.g2 = gamma2; p.g3 = gamma3; p.mask = mask; p.unorm = unorm; p.sim = const_cast<float *>(sim);
@@ -1130,7 +1188,10 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
     p.nw = nw; p.order = order; p.koff = koff; p.kbase = kbase;
     p.i0 = (int)s0; p.kc = kc; p.row_lse = row_lse; p.col_lse = col_lse; p.gscale = scal;
     p.labels = labels; p.row_offset = row_offset; p.b_total = b_total; p.kq = kq;
-    p.x_ds = x_ds; p.x_a = hmat ? x_a : nullptr; p.svec = svec; p.scale_ds = scale_ds; p.scale_ba = scale_ba;
+    p.x_ds = x_ds; p.store_e = hmat ? 1 : 0; p.svec = svec; p.scale_ds = scale_ds; p.scale_e = scale_e;
+    if (hmat && (rc = make_map_f16_box(&tl.tmE, x_e, (uint64_t)r, (uint64_t)bc, (uint64_t)kc, (uint64_t)rp,
+                                       (uint64_t)(bc * rp), 1, 16)))
+      return rc;
 #ifdef DAMSM_TC_DEBUG
     p.dbg = getenv("DAMSM_DBG") ? atoi(getenv("DAMSM_DBG")) : 0;
 #endif
@@ -1182,7 +1243,7 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
       if ((rc = launch_gemm_tc(g, st))) return rc;
     }
     // H_j (R x R) += sum_k s_k A_j[:,k] A_j[:,k]^T: own tcgen05 kernel (hmat_tc.cu), one CTA per image
-    if (hmat && (rc = launch_hmat_tc(x_a, svec, bc, r, kc, scal + 4, hmat, st))) return rc;
+    if (hmat && (rc = launch_hmat_tc(x_e, rp, svec, bc, r, kc, scal + 4, hmat, st))) return rc;
   }
   return 0;
 }

@@ -3,6 +3,8 @@ import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 pkg = importlib.import_module("t2i_clip-gan_b200")
+if os.environ.get("DAMSM_AB_LIB"):
+    importlib.import_module("t2i_clip-gan_b200._lib").LIB_PATH = os.path.abspath(os.environ["DAMSM_AB_LIB"])
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 296
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 77          # every caption has this many words
 T, R, D = 77, 196, 512
