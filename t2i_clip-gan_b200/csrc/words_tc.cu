@@ -79,6 +79,14 @@ __host__ __device__ inline TcLayout tc_layout(int NT, int R, int D) {
 #define TRACEW(p, it, k) do {} while (0)
 #endif
 
+// Backward: TMA store maps of the two scratch matrices of the current chunk, one per caption length (nw / 16 - 1): the
+// box of a store covers exactly the caption's words (rows of x_e / columns of x_ds), so that a pair's tile leaves the
+// chip with 4 + 1 instructions (the store unit's cost is per row piece, not per byte: few large boxes, not many small ones).
+struct TcStoreMaps {
+  CUtensorMap e[8];   // x_e  [(caption, word)][(image, region)]: box 64 regions x 1 image x nw words, 128-byte swizzle
+  CUtensorMap d[8];   // x_ds [(image, region)][(caption, word)]: box nw words x ceil8(R) regions x 1 image, dense rows
+};
+
 struct TcParams {
   int br, bc, T, R, D;
   int img_per_cta;
@@ -230,7 +238,7 @@ template <int NT, bool BWD, int NW, int CL>
 __global__ void __launch_bounds__(NW * 32, 1)
 words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
                 const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmV2,
-                const __grid_constant__ CUtensorMap tmG2, const __grid_constant__ CUtensorMap tmE, TcParams p) {
+                const __grid_constant__ CUtensorMap tmG2, const __grid_constant__ TcStoreMaps tmS, TcParams p) {
   constexpr int NH = NT / 2;                 // words per softmax thread
   constexpr int TC_THREADS = NW * 32;
   constexpr int TMA_WARP = (NW == 16) ? 7 : 16;
@@ -252,6 +260,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t *coef_full = q_full + 8;                                              // 14,15 (backward: coefficients of even / odd pairs published)
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 16);
   uint64_t *e2_free = bars + 17;                                                 // backward: the e2 operand has left the chip
+  uint64_t *ds_ready = bars + 18, *ds_free = bars + 19;                          // backward: dS tile staged / stored
   float *vu = reinterpret_cast<float *>(misc + 256);          // [NT] ||qhat_t||
   float *tb = vu + NT;                                        // 0 for real words, -inf for padding and t >= T
   float *tb2 = tb + NT;                                       // 0 for t < T, -inf for t >= T
@@ -280,7 +289,8 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // word serialise and were the longest item of the per-pair critical path
     mbar_init(&s_free[0], L.act_warps); mbar_init(&s_free[1], L.act_warps);
     mbar_init(e2_ready, L.act_warps); mbar_init(m_free, L.act_warps);
-    if constexpr (BWD) { mbar_init(&coef_full[0], L.act_warps); mbar_init(&coef_full[1], L.act_warps); mbar_init(e2_free, 1); }
+    if constexpr (BWD) { mbar_init(&coef_full[0], L.act_warps); mbar_init(&coef_full[1], L.act_warps); mbar_init(e2_free, 1);
+                         mbar_init(ds_ready, L.act_warps); mbar_init(ds_free, 1); }
     else mbar_init(red_full, L.act_warps);
     fence_barrier_init();
   }
@@ -422,19 +432,18 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_commit(m_full);
         TRACE(p, 0, it, 3);
       };
-      // backward: the fp16 e2 operand of GEMM2 (words x regions, exactly what the tensor core multiplied) IS the second
-      // scratch matrix: once GEMM2 has read it, 16-word boxes go from shared memory to x_e[(caption, word)][(image, region)]
-      // by TMA -- no register-path stores, no instructions in the softmax warps.  The H kernel folds 1/Y^2 into its
-      // per-word scale (A = e2 / Y).
-      auto estore = [&](int it) {
-        mbar_spin(m_full, it & 1);                                   // GEMM2 of this pair has consumed the operand
+      // backward: sweep 2 stages the scaled fp16 dS tile of the pair in the e2 buffer, [region][nw words]; it goes to
+      // x_ds[(image, region)][(caption, word)] as ONE TMA store: whole row segments instead of 16-byte pieces of 32
+      // different rows per warp-level store (the register-path stores were 26 % of this kernel).
+      auto dsstore = [&](int it) {
+        mbar_spin(ds_ready, it & 1);
+        TRACE(p, 0, it, 4);
         const int krow = (int)(p.koff[spos] - p.kbase);
-        for (int kb = 0; kb < L.nkb_r; ++kb)
-          for (int m = 0; m < NTi; m += 16)
-            tma_store_3d(&tmE, E2 + kb * NT * 128 + m * 128, kb * 64, j0 + it, krow + m);
+        tma_store_3d(&tmS.d[(NTi >> 4) - 1], E2, krow, 0, j0 + it);
         bulk_commit_group();
-        bulk_wait_group_read0();                                     // shared memory has been read: B1 may overwrite it
-        mbar_arrive(e2_free);
+        bulk_wait_group_read0();                                     // B1 of the next pair may overwrite the buffer
+        TRACE(p, 0, it, 5);
+        mbar_arrive(ds_free);
       };
       const int n = j1 - j0;
       if (nbuf == 2 && !BWD) {
@@ -446,10 +455,10 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       } else {
         for (int it = 0; it < n; ++it) {
           gemm1(it);
-          if (BWD && p.store_e && it > 0) estore(it - 1);
+          if (BWD && it > 0) dsstore(it - 1);
           gemm2(it);
         }
-        if (BWD && p.store_e && n > 0) { estore(n - 1); bulk_wait_group0(); }
+        if (BWD && n > 0) { dsstore(n - 1); bulk_wait_group0(); }
       }
     }
   } else if (warp < 16 && (warp & 7) < L.act_warps / 2) {
@@ -463,6 +472,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bool valid = rg < R;
     const uint32_t rowmask = valid ? 0xffffffffu : 0u;
     const bool k_row = rg < L.k2_steps * 16;                        // row lies inside GEMM2's K range
+    const int e_warp = min(3, L.act_warps / 2 - 1);                 // backward: the warp whose lane 0 issues the e2 stores
     // shared-memory address of e2[t = c0][r' = rg] and the 8 swizzle variants (t & 7)
     uint32_t e2a[8];
     {
@@ -475,7 +485,10 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // cross-warp partial sums, laid out [parity][word t][8 warps of that word's half] so the tail reads float4s
     float *red1w0 = red1 + c0 * 8 + (warp & 7), *red2w0 = red2 + c0 * 8 + (warp & 7);
     const int widx = (warp & 7) * 32 + lane;                        // row slot in zbuf / wbuf
-    constexpr int CPL = (NT + 31) / 32;                             // words per lane in the one-warp sections
+    // per-word scalar work (forward tail, backward coefficients) is spread over the softmax warps: a few words per warp,
+    // one lane per word
+    const int cwarp = (warp & 7) + (warp >> 3) * (L.act_warps / 2); // 0 .. act_warps-1
+    const int cwords = (NT + L.act_warps - 1) / L.act_warps;        // words per warp (<= 32)
     // backward: per-row constants of dL/dsim (both cross-entropies, losses.py:265-269), kept in shared memory (every
     // softmax warp reads them once per pair in bwd_coef; registers are the scarce resource of this kernel).
     // The upstream gradients enter normalised by their larger magnitude, which is folded back into the GEMM / H
@@ -483,9 +496,14 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // (LAMBDA = 50 in clip_coco_DMGAN.yml, an AMP loss scale of 2^16, ...)
     float *bwc = reinterpret_cast<float *>(misc + 160);             // [0] row_lse, [1] g0/B, [2] g1/B, [3] |g| max
     int64_t *bwl = reinterpret_cast<int64_t *>(misc + 176);         // [0] label of this row, [1] global row index
-    // ---- serial tail of the forward, one warp: per-word cosine (losses.py:197-198), gamma2 log-sum-exp (:199-203),
-    //      statistics for the backward.  It runs one pair late, while GEMM2 of the next pair is in flight (every warp
-    //      idles there), so it is off the critical path; the bookkeeping it reads is double-buffered by pair parity.
+    // ---- tail of the forward: per-word cosine (losses.py:197-198), gamma2 log-sum-exp (:199-203), statistics for the
+    //      backward.  It runs one pair late, while GEMM2 of the next pair is in flight, and is SPREAD over the softmax warps
+    //      (one lane per word): run by warp 0 alone, its ~2 k cycles made warp 0 the last to deliver e2 for every pair.
+    //      |rho| <= 1 up to rounding, so the log-sum-exp uses the fixed shift gamma2 (the reference exponentiates without
+    //      any shift); the warps' partial sums meet in shared memory and the last warp to arrive writes the score.  The
+    //      bookkeeping is triple-buffered by pair index.
+    float *tailp = vc;                                              // [3][16] partial sums (vc is backward-only)
+    int *tailc = reinterpret_cast<int *>(vc + 48);                  // [3] arrival counters (zero-initialised with vc)
     auto fwd_tail = [&](int it_, int j_) {
       const int rb_ = it_ % 3;
       mbar_wait(red_full, it_ & 1);
@@ -493,34 +511,35 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float4 *r2 = reinterpret_cast<const float4 *>(red2 + rb_ * NT * 8);
       const float *vYb_ = vY + rb_ * NT;
       const int64_t pair = (int64_t)i * p.bc + j_;
-      float *st = p.stats ? p.stats + pair * 3 * T : nullptr;
-      float xv[CPL];
-      float mx = -INFINITY;
-      const int tmax = min(T, NTi);
-#pragma unroll
-      for (int q = 0; q < CPL; ++q) {
-        const int t = q * 32 + lane;
-        xv[q] = -INFINITY;
-        if (t < tmax) {
-          const float4 a0 = r1[2 * t], a1 = r1[2 * t + 1], b0 = r2[2 * t], b1 = r2[2 * t + 1];
-          const float np = ((a0.x + a0.y) + (a0.z + a0.w)) + ((a1.x + a1.y) + (a1.z + a1.w));
-          const float nn = ((b0.x + b0.y) + (b0.z + b0.w)) + ((b1.x + b1.y) + (b1.z + b1.w));
-          const float iy = 1.f / vYb_[t];
-          const float n = sqrtf(fmaxf(nn, 0.f)) * iy;
-          const float rho = (np * iy) / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
-          if (st) { st[t] = rho; st[T + t] = n; st[2 * T + t] = iy; }
-          xv[q] = p.g2 * rho;
-          mx = fmaxf(mx, xv[q]);
+      const int t = cwarp * cwords + lane;
+      float e = 0.f;
+      if (lane < cwords && t < min(T, NTi)) {
+        const float4 a0 = r1[2 * t], a1 = r1[2 * t + 1], b0 = r2[2 * t], b1 = r2[2 * t + 1];
+        const float np = ((a0.x + a0.y) + (a0.z + a0.w)) + ((a1.x + a1.y) + (a1.z + a1.w));
+        const float nn = ((b0.x + b0.y) + (b0.z + b0.w)) + ((b1.x + b1.y) + (b1.z + b1.w));
+        const float iy = 1.f / vYb_[t];
+        const float n = sqrtf(fmaxf(nn, 0.f)) * iy;
+        const float rho = (np * iy) / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
+        if (p.stats) {
+          float *st = p.stats + pair * 3 * T;
+          st[t] = rho; st[T + t] = n; st[2 * T + t] = iy;
+        }
+        e = __expf(p.g2 * rho - p.g2);
+      }
+      e = warp_sum(e);
+      if (lane == 0) {
+        tailp[rb_ * 16 + cwarp] = e;
+        __threadfence_block();
+        if (atomicAdd(&tailc[rb_], 1) == L.act_warps - 1) {         // every warp's partial sum is in: finish the score
+          __threadfence_block();
+          tailc[rb_] = 0;
+          float se = 0.f;
+          for (int w = 0; w < L.act_warps; ++w) se += tailp[rb_ * 16 + w];   // fixed order: deterministic
+          // words t >= nw[i] (all padding): their exp(gamma2 rho_bar) sum comes from the closed form
+          if (p.epad && NTi < T) se += p.epad[pair] * __expf(-p.g2);
+          p.sim[pair] = p.g3 * ((__logf(se) + p.g2) / p.g2);
         }
       }
-      mx = warp_max(mx);
-      float se = 0.f;
-#pragma unroll
-      for (int q = 0; q < CPL; ++q) se += __expf(xv[q] - mx);       // exp(-inf) = 0 for the unused slots
-      se = warp_sum(se);
-      // words t >= nw[i] (all padding): their exp(gamma2 rho_bar) sum comes from the closed form (|gamma2 rho| <= gamma2)
-      if (p.epad && NTi < T) se += p.epad[pair] * __expf(-mx);
-      if (lane == 0) p.sim[pair] = p.g3 * ((__logf(se) + mx) / p.g2);
     };
     // ---- pass A of pair `it_`: e1 = exp(S + mask bias), Z = sum_t e1 (softmax over words, losses.py:127,143-144).
     //      Forward runs it for the NEXT pair while GEMM2 of the current one is in flight (e1 of the current pair is
@@ -567,8 +586,6 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     //      after GEMM2, and one pair ahead it still made warp 0 the slowest warp of every pair.  Two barriers /
     //      coefficient buffers by pair parity; a buffer is rewritten only after every warp has left the sweeps of pair
     //      it_-2 (m_free).
-    const int cwarp = (warp & 7) + (warp >> 3) * (L.act_warps / 2);          // 0 .. act_warps-1
-    const int cwords = (NT + L.act_warps - 1) / L.act_warps;                  // words per warp (<= 32)
     auto bwd_coef = [&](int it_, int j_) {
       float *vcb_ = vc + (it_ & 1) * 4 * NT;
       const int64_t pair = (int64_t)i * p.bc + j_;
@@ -639,8 +656,9 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       //      forward also forms the N' = sum_r e2 S partial sums ----
       // B1 (critical path): e2 for every owned word -> fp16 -> the B operand of GEMM2, then GEMM2 can start.
       if constexpr (BWD) {
-        if (p.store_e && it > 0) mbar_wait(e2_free, (it - 1) & 1);  // the previous pair's e2 has been stored
+        if (it > 0) mbar_wait(ds_free, (it - 1) & 1);               // the previous pair's dS tile has left the buffer
       }
+      TRACEW(p, it, 3);
 #pragma unroll
       for (int tl = 0; tl < NH; tl += 2) {
         if (DBG(p, 32)) break;
@@ -698,10 +716,23 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (warp == 1 && lane == 0) TRACE(p, 1, it, 2);
       if constexpr (!BWD) {
         if (j + 1 < j1) pass_a(it + 1);                             // fills the GEMM2 bubble
-        if (warp == 0 && it > 0) fwd_tail(it - 1, j - 1);
+        if (it > 0) fwd_tail(it - 1, j - 1);
       }
       mbar_wait(m_full, it & 1);
-      if constexpr (BWD) mbar_wait(&coef_full[it & 1], (it >> 1) & 1);
+      if constexpr (BWD) {
+        // The fp16 e2 operand of GEMM2 (words x regions, exactly what the tensor core multiplied) IS the second scratch
+        // matrix: once GEMM2 has read it, 16-word boxes go from shared memory to x_e[(caption, word)][(image, region)] by
+        // TMA -- no register-path stores.  The H kernel folds 1/Y^2 into its per-word scale (A = e2 / Y).  Issued by one
+        // lane of a warp on the lightly loaded fourth scheduler; the buffer is reused by sweep 2 (dS staging) once the
+        // stores have read it.
+        if (p.store_e && warp == e_warp && lane == 0) {
+          const int krow = (int)(p.koff[spos] - p.kbase);
+          for (int kb = 0; kb < L.nkb_r; ++kb)
+            tma_store_3d(&tmS.e[(NTi >> 4) - 1], E2 + kb * NT * 128, kb * 64, j, krow);
+          bulk_commit_group();
+        }
+        mbar_wait(&coef_full[it & 1], (it >> 1) & 1);
+      }
       if (warp == 1 && lane == 0) TRACE(p, 1, it, 3);
       tc_fence_after();
       if constexpr (!BWD) {
@@ -763,10 +794,16 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         named_bar_sync(2 + (warp & 7), 64);
         const float2 nW = f2(-(wb[widx] + wb[256 + widx]));          // -sp W
         // ---- sp dS = cz f + P (sp dP - sp W); A = f / Y  -> fp16 rows of the scratch matrices ----
+        if (p.store_e) {                                             // e2 of this pair has left the buffer (TMA store)
+          if (warp == e_warp) {
+            if (lane == 0) { TRACE(p, 1, it, 5); bulk_wait_group_read0(); TRACE(p, 1, it, 6); mbar_arrive(e2_free); }
+            __syncwarp();
+          }
+          mbar_wait(e2_free, it & 1);
+        }
         if (!DBG(p, 2)) {
-          const int64_t row = (int64_t)j * R + (valid ? rg : 0);
-          const int64_t off = row * p.kc + (p.koff[spos] - p.kbase) + c0;
-          uint4 *o_ds = reinterpret_cast<uint4 *>(p.x_ds + off);
+          // staging address of this thread's row: [region][nw words]
+          uint8_t *o_ds = E2 + (valid ? rg : 0) * (NTi * 2) + c0 * 2;
 #pragma unroll
           for (int c = 0; c < NH / 8; ++c) {
             if (c * 8 < nh) {                                        // CTA-uniform: tcgen05.ld is warp-collective
@@ -787,24 +824,27 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 pk_ds[k >> 1] = pack_half2_sat(ds.x, ds.y);
               }
               if (valid && !DBG(p, 1)) {
-                // streaming stores: the scratch is written once and read back by the GEMMs much later
-                __stcs(o_ds + c, make_uint4(pk_ds[0], pk_ds[1], pk_ds[2], pk_ds[3]));
+                *reinterpret_cast<uint4 *>(o_ds + c * 16) = make_uint4(pk_ds[0], pk_ds[1], pk_ds[2], pk_ds[3]);
               }
             }
           }
         }
         }
         TRACEW(p, it, 5);
+        fence_proxy_async_smem();                                    // the staged dS tile is read by the TMA store
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
+          mbar_arrive(ds_ready);
           mbar_arrive(&s_free[b]);
           mbar_arrive(m_free);
         }
       }
     }
     if constexpr (!BWD) {
-      if (warp == 0 && j1 > j0) fwd_tail(j1 - j0 - 1, j1 - 1);
+      if (j1 > j0) fwd_tail(j1 - j0 - 1, j1 - 1);
+    } else {
+      if (warp == e_warp && lane == 0) bulk_wait_group0();
     }
   }
   tc_fence_before();
@@ -849,17 +889,17 @@ int make_map_f16(CUtensorMap *m, const void *base, uint64_t n0, uint64_t n1, uin
 
 // fp16 tensor (n2, n1, n0) with explicit box (b2, b1, b0 = 64), 128-byte swizzle
 int make_map_f16_box(CUtensorMap *m, const void *base, uint64_t n0, uint64_t n1, uint64_t n2, uint64_t pitch1_elems,
-                     uint64_t pitch2_elems, uint32_t box1, uint32_t box2) {
+                     uint64_t pitch2_elems, uint32_t box1, uint32_t box2, uint32_t box0 = 64, bool swizzle = true) {
   PFN_encodeTiled enc = get_encode();
   DAMSM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[3] = {n0, n1, n2};
   cuuint64_t strides[2] = {pitch1_elems * 2, pitch2_elems * 2};
-  cuuint32_t box[3] = {64, box1, box2};
+  cuuint32_t box[3] = {box0, box1, box2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  DAMSM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) dims=(%llu,%llu,%llu) box=(64,%u,%u)", (int)r,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DAMSM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) dims=(%llu,%llu,%llu) box=(..,%u,%u)", (int)r,
                 (unsigned long long)n0, (unsigned long long)n1, (unsigned long long)n2, box1, box2);
   return 0;
 }
@@ -889,7 +929,7 @@ struct TcLaunch {
   int nt;
   TcLayout L;
   CUtensorMap tmQ, tmV, tmG, tmV2, tmG2, tmVh, tmGh;   // full-row boxes; cluster mode: second / first half-row boxes
-  CUtensorMap tmE;                                     // backward: store map of the e2 scratch of the current chunk
+  TcStoreMaps tmS;                                     // backward: store maps of the e2 / dS scratch of the current chunk
   int sms;
   bool cluster_ok;
 };
@@ -914,7 +954,7 @@ static int tc_prepare(TcLaunch *tl, const char *who, const void *qhat16, int64_t
   if ((rc = make_map_f16(&tl->tmV, vhat16, d, r, bc, d, r * d, tl->L.rs))) return rc;
   if ((rc = make_map_f16(&tl->tmG, gx, rk, r + 1, bc, rk, (r + 1) * rk, tl->L.rs))) return rc;
   // cluster mode (pairs of captions share the image stream): half-row boxes for the two CTAs of a cluster
-  tl->tmV2 = tl->tmV; tl->tmG2 = tl->tmG; tl->tmE = tl->tmQ;
+  tl->tmV2 = tl->tmV; tl->tmG2 = tl->tmG; for (int v = 0; v < 8; ++v) tl->tmS.e[v] = tl->tmS.d[v] = tl->tmQ;
   tl->cluster_ok = tl->nt == 80 && tl->L.act_warps <= 14 && tl->L.rs - tl->L.rs_half >= 8 && !getenv("DAMSM_TC_NO_CLUSTER");
   if (tl->cluster_ok) {
     CUtensorMap a, b;
@@ -957,11 +997,11 @@ static int tc_launch(const TcLaunch &tl, TcParams &p, int64_t rows, cudaStream_t
     if (tl.L.act_warps <= 14) {                                                                                       \
       DAMSM_CUDA(cudaFuncSetAttribute(words_tc_kernel<NT_, BWD, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)tl.L.total));                                                              \
-      words_tc_kernel<NT_, BWD, 16, 1><<<grid, 16 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, tl.tmV, tl.tmG, tl.tmE, p); \
+      words_tc_kernel<NT_, BWD, 16, 1><<<grid, 16 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, tl.tmV, tl.tmG, tl.tmS, p); \
     } else {                                                                                                          \
       DAMSM_CUDA(cudaFuncSetAttribute(words_tc_kernel<NT_, BWD, 18, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)tl.L.total));                                                              \
-      words_tc_kernel<NT_, BWD, 18, 1><<<grid, 18 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, tl.tmV, tl.tmG, tl.tmE, p); \
+      words_tc_kernel<NT_, BWD, 18, 1><<<grid, 18 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, tl.tmV, tl.tmG, tl.tmS, p); \
     }                                                                                                                 \
   } while (0)
   // forward: always when possible; backward: opt-in (DAMSM_TC_CLUSTER_BWD=1) -- its kernel is bound by the softmax
@@ -976,7 +1016,7 @@ static int tc_launch(const TcLaunch &tl, TcParams &p, int64_t rows, cudaStream_t
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    DAMSM_CUDA(cudaLaunchKernelEx(&cfg, kern, tl.tmQ, tl.tmVh, tl.tmGh, tl.tmV2, tl.tmG2, tl.tmE, p));
+    DAMSM_CUDA(cudaLaunchKernelEx(&cfg, kern, tl.tmQ, tl.tmVh, tl.tmGh, tl.tmV2, tl.tmG2, tl.tmS, p));
     return check_launch(BWD ? "words_bwd_tc (fused recompute, 2-CTA clusters)" : "words_fwd_tc (2-CTA clusters)");
   }
   switch (tl.nt) {
@@ -1128,8 +1168,9 @@ extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void
 extern "C" int64_t damsm_words_bwd_tc_fixed_bytes(void) { return TC_SCAL_BYTES; }
 
 // bytes of scratch per K column (= one word of one caption of a chunk): the fp16 dS matrix [(j,r)][k], the fp16 e2 matrix
-// [k][(j, r padded to a multiple of 8)] and the per-word scales (bc) fp32
-static inline int64_t tc_e_pitch(int64_t r) { return (r + 7) / 8 * 8; }
+// [k][(j, r padded to a multiple of 64: every 64-region box row of the TMA store is then one aligned 128-byte line)] and
+// the per-word scales (bc) fp32
+static inline int64_t tc_e_pitch(int64_t r) { return (r + 63) / 64 * 64; }
 extern "C" int64_t damsm_words_bwd_tc_col_bytes(int64_t bc, int64_t r) { return bc * r * 2 + bc * tc_e_pitch(r) * 2 + bc * 4; }
 
 extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
@@ -1189,9 +1230,15 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
     p.i0 = (int)s0; p.kc = kc; p.row_lse = row_lse; p.col_lse = col_lse; p.gscale = scal;
     p.labels = labels; p.row_offset = row_offset; p.b_total = b_total; p.kq = kq;
     p.x_ds = x_ds; p.store_e = hmat ? 1 : 0; p.svec = svec; p.scale_ds = scale_ds; p.scale_e = scale_e;
-    if (hmat && (rc = make_map_f16_box(&tl.tmE, x_e, (uint64_t)r, (uint64_t)bc, (uint64_t)kc, (uint64_t)rp,
-                                       (uint64_t)(bc * rp), 1, 16)))
-      return rc;
+    for (int v = 0; v < tl.nt / 16; ++v) {
+      const uint32_t nwv = 16u * (v + 1);
+      if ((rc = make_map_f16_box(&tl.tmS.d[v], x_ds, (uint64_t)kc, (uint64_t)r, (uint64_t)bc, (uint64_t)kc, (uint64_t)(r * kc),
+                                 (uint32_t)((r + 7) / 8 * 8), 1, nwv, false)))
+        return rc;
+      if (hmat && (rc = make_map_f16_box(&tl.tmS.e[v], x_e, (uint64_t)rp, (uint64_t)bc, (uint64_t)kc, (uint64_t)rp,
+                                         (uint64_t)(bc * rp), 1, nwv)))
+        return rc;
+    }
 #ifdef DAMSM_TC_DEBUG
     p.dbg = getenv("DAMSM_DBG") ? atoi(getenv("DAMSM_DBG")) : 0;
 #endif
@@ -1213,13 +1260,15 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
       long long t0 = h[(1 * 16 + 0) * 8 + 0];
       fprintf(stderr, "bwd trace chunk %lld block %d (cycles since the first pass A):\n", (long long)c, p.trace_block);
       for (int w = 0; w < 16; ++w)
-        fprintf(stderr, "warp %2d it6: top %7lld passA %7lld e2arrive %7lld m_full %7lld sweeps_end %7lld\n", w,
-                h[(2 * 16 + w) * 8 + 0] - t0, h[(2 * 16 + w) * 8 + 1] - t0, h[(2 * 16 + w) * 8 + 2] - t0, h[(2 * 16 + w) * 8 + 4] - t0,
+        fprintf(stderr, "warp %2d it6: top %7lld passA %7lld dsfree %7lld e2arrive %7lld m_full %7lld sweeps_end %7lld\n", w,
+                h[(2 * 16 + w) * 8 + 0] - t0, h[(2 * 16 + w) * 8 + 1] - t0, h[(2 * 16 + w) * 8 + 3] - t0, h[(2 * 16 + w) * 8 + 2] - t0, h[(2 * 16 + w) * 8 + 4] - t0,
                 h[(2 * 16 + w) * 8 + 5] - t0);
       for (int it = 0; it < 12; ++it)
-        fprintf(stderr, "it %2d MMA: g1start %7lld g1issued %7lld g2start %7lld g2issued %7lld | SM: top %7lld passA %7lld B1+coef %7lld m_full %7lld sweeps %7lld\n", it,
+        fprintf(stderr, "it %2d MMA: g1start %7lld g1issued %7lld g2start %7lld g2issued %7lld ds_ready %7lld ds_read %7lld | SM: top %7lld passA %7lld B1+coef %7lld m_full %7lld | e_wait %7lld e_read %7lld\n", it,
                 h[(0 * 16 + it) * 8 + 0] - t0, h[(0 * 16 + it) * 8 + 1] - t0, h[(0 * 16 + it) * 8 + 2] - t0, h[(0 * 16 + it) * 8 + 3] - t0,
-                h[(1 * 16 + it) * 8 + 0] - t0, h[(1 * 16 + it) * 8 + 1] - t0, h[(1 * 16 + it) * 8 + 2] - t0, h[(1 * 16 + it) * 8 + 3] - t0, h[(1 * 16 + it) * 8 + 4] - t0);
+                h[(0 * 16 + it) * 8 + 4] - t0, h[(0 * 16 + it) * 8 + 5] - t0,
+                h[(1 * 16 + it) * 8 + 0] - t0, h[(1 * 16 + it) * 8 + 1] - t0, h[(1 * 16 + it) * 8 + 2] - t0, h[(1 * 16 + it) * 8 + 3] - t0,
+                h[(1 * 16 + it) * 8 + 5] - t0, h[(1 * 16 + it) * 8 + 6] - t0);
     }
     // development builds only: time the fused recompute kernel alone / stop after it (results are then incomplete)
     if (getenv("DAMSM_BWD_FUSED_ONLY")) continue;
