@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(HM_THREADS, 1) hmat_tc_kernel(const __grid_con
 }
 
 int make_map_f16_box(CUtensorMap *m, const void *base, uint64_t n0, uint64_t n1, uint64_t n2, uint64_t pitch1_elems,
-                     uint64_t pitch2_elems, uint32_t box1, uint32_t box2, uint32_t box0, bool swizzle);   // words_tc.cu
+                     uint64_t pitch2_elems, uint32_t box1, uint32_t box2, uint32_t box0, bool swizzle, bool swizzle32);   // words_tc.cu
 
 // x_e: (kc, bc * rp) fp16 row-major scratch (image j's regions at columns [j*rp, j*rp + R)); svec (bc, kc); hmat (bc, R, R)
 // accumulated
@@ -204,7 +204,7 @@ int launch_hmat_tc(const void *x_e, int64_t rp, const float *svec, int64_t bc, i
   const uint32_t total = (HM_SA + HM_SB) * stage_bytes + 2 * HM_CH_BYTES + 256 + HM_SB * 64 * 4 + 1024;
   CUtensorMap tmE;
   int rc;
-  if ((rc = make_map_f16_box(&tmE, x_e, (uint64_t)r, (uint64_t)bc, (uint64_t)kc, (uint64_t)rp, (uint64_t)(bc * rp), 1, 64, 64, true)))
+  if ((rc = make_map_f16_box(&tmE, x_e, (uint64_t)r, (uint64_t)bc, (uint64_t)kc, (uint64_t)rp, (uint64_t)(bc * rp), 1, 64, 64, true, false)))
     return rc;
   int dev = 0, max_optin = 0;
   DAMSM_CUDA(cudaGetDevice(&dev));

@@ -189,6 +189,17 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                            // layout type: SWIZZLE_128B
   return d;
 }
+// Same for rows of 32 B (16 halves = one K = 16 step) with the 32-byte swizzle (TMA SWIZZLE_32B): 8-row groups are 256 B
+// apart, layout type 6.
+__device__ __forceinline__ uint64_t umma_desc_k_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16 with fp16 A/B (both K-major; format code 0 = F16, 1 would be BF16),
 // fp32 accumulate, M=128, N=n.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
@@ -216,6 +227,19 @@ __device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
       :
       : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// same, the A descriptor with its own high word (another layout than B's)
+__device__ __forceinline__ void umma_f16_lohi2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed

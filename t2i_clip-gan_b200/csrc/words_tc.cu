@@ -39,7 +39,9 @@ struct TcLayout {
   int nkb_d, nkb_r;  // 64-wide k-blocks of GEMM1 / GEMM2
   int nbuf;          // S accumulators in TMEM (2 when 3*tiles*NT <= 512 columns)
   int act_warps;     // softmax warps that own at least one row below max(16*k2_steps, R+1)
-  uint32_t q_bytes, stage_bytes, e2_bytes, misc_off, total;
+  int tail1;         // the last k-block of GEMM2 is a single K=16 step (R = 196: 13 steps): its Gx columns get a buffer of
+                     // their own (32-byte rows, 32-byte swizzle) instead of a fourth slot-sized block through the 3-slot ring
+  uint32_t q_bytes, stage_bytes, e2_bytes, tail_off, tail_bytes, misc_off, total;
 };
 
 __host__ __device__ inline TcLayout tc_layout(int NT, int R, int D) {
@@ -60,10 +62,15 @@ __host__ __device__ inline TcLayout tc_layout(int NT, int R, int D) {
   // stage.  Their TMEM lanes are never used, but the bytes must be finite fp16 (zero-initialised / operand data):
   // the overrun of the last stage may reach into the e2 buffer but not into the fp32 bookkeeping behind it.
   if ((uint32_t)l.tiles * 16384 > l.stage_bytes + l.e2_bytes) l.stage_bytes = (uint32_t)l.tiles * 16384;
-  l.misc_off = l.q_bytes + TC_STAGES * l.stage_bytes + l.e2_bytes;
-  // misc: 256 B of barriers / scalars, then floats: u,tb,tb2 [NT] + iy [2][NT] + Y [3][NT] + vc float4 [2][NT] +
-  // red1/red2 [3][NT][8] + zbuf/wbuf [2][2][256]   ([2]/[3] = multi-buffered by pair index, see fwd_tail)
-  l.total = l.misc_off + 256 + 4 * (8 * NT + 8 * NT + 48 * NT + 2048) + 1024 /*alignment slack*/;
+  l.tail1 = (l.k2_steps % 4 == 1 && l.nkb_r > 1) ? 1 : 0;
+  l.tail_off = l.q_bytes + TC_STAGES * l.stage_bytes + l.e2_bytes;
+  l.tail_bytes = l.tail1 ? (uint32_t)l.tiles * 128 * 32 : 0;       // all M rows of the MMAs: rows past `rs` stay zero
+  l.misc_off = l.tail_off + l.tail_bytes;
+  // misc: 256 B of barriers / scalars, then floats: u,tb,tb2 [NT] + zbuf [2][2][256] and
+  //   forward:  Y [3][NT] + red1/red2 [3][NT][8] + tail partial sums [64]   ([3] = buffered by pair index, see fwd_tail)
+  //   backward: coefficients [2][4][NT] + wbuf [2][2][256]
+  const uint32_t fl_fwd = 3 * NT + 1024 + 3 * NT + 48 * NT + 64, fl_bwd = 3 * NT + 1024 + 8 * NT + 1024;
+  l.total = l.misc_off + 256 + 4 * (fl_fwd > fl_bwd ? fl_fwd : fl_bwd) + 1024 /*alignment slack*/;
   return l;
 }
 
@@ -238,7 +245,8 @@ template <int NT, bool BWD, int NW, int CL>
 __global__ void __launch_bounds__(NW * 32, 1)
 words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
                 const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmV2,
-                const __grid_constant__ CUtensorMap tmG2, const __grid_constant__ TcStoreMaps tmS, TcParams p) {
+                const __grid_constant__ CUtensorMap tmG2, const __grid_constant__ CUtensorMap tmGt,
+                const __grid_constant__ TcStoreMaps tmS, TcParams p) {
   constexpr int NH = NT / 2;                 // words per softmax thread
   constexpr int TC_THREADS = NW * 32;
   constexpr int TMA_WARP = (NW == 16) ? 7 : 16;
@@ -264,10 +272,15 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float *vu = reinterpret_cast<float *>(misc + 256);          // [NT] ||qhat_t||
   float *tb = vu + NT;                                        // 0 for real words, -inf for padding and t >= T
   float *tb2 = tb + NT;                                       // 0 for t < T, -inf for t >= T
-  float *viy = tb2 + NT, *vY = viy + 2 * NT;                  // 1/Y [2][NT] (backward), Y [3][NT] (forward)
-  float *vc = vY + 3 * NT;                                    // backward coefficients [2][4][NT]: sp*cx, -sp*cy, cz, (unused)
-  float *red1 = vc + 8 * NT, *red2 = red1 + 24 * NT;          // [3][NT][8] each
-  float *zbuf = red2 + 24 * NT, *wbuf = zbuf + 1024;          // [2 parities][2 halves][256] each
+  float *zbuf = tb2 + NT;                                     // [2 parities][2 halves][256]
+  float *dirf = zbuf + 1024;                                  // direction-specific part
+  float *vY = dirf;                                           // forward: Y [3][NT]
+  float *red1 = vY + 3 * NT, *red2 = red1 + 24 * NT;          // forward: [3][NT][8] each
+  float *tailp = red2 + 24 * NT;                              // forward: [3][16] partial sums + [3] counters (fwd_tail)
+  float *vc = dirf;                                           // backward coefficients [2][4][NT]: sp*cx, -sp*cy, cz, (unused)
+  float *wbuf = vc + 8 * NT;                                  // backward: [2 parities][2 halves][256]
+  uint8_t *GT = smem + L.tail_off;                            // Gx tail block (L.tail1)
+  uint64_t *tail_full = bars + 20, *tail_empty = bars + 21;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int spos = (BWD ? p.i0 : 0) + blockIdx.x;                  // position in the sorted caption order
@@ -284,6 +297,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     *reinterpret_cast<uint4 *>(smem + o) = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
+    mbar_init(tail_full, 1); mbar_init(tail_empty, 1);
     mbar_init(q_full, 1); mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(m_full, 1);
     // the softmax warps arrive once per warp (lane 0 after __syncwarp): 448 per-thread arrivals on one shared-memory
     // word serialise and were the longest item of the per-pair critical path
@@ -299,13 +313,16 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     vu[t] = in ? p.unorm[(int64_t)i * T + t] : 1.f;
     tb[t] = (in && p.mask[(int64_t)i * T + t]) ? 0.f : -INFINITY;
     tb2[t] = in ? 0.f : -INFINITY;
-    for (int k = 0; k < 8; ++k) vc[k * NT + t] = 0.f;
-    viy[t] = viy[NT + t] = 0.f;
-    for (int k = 0; k < 24; ++k) red1[t * 24 + k] = red2[t * 24 + k] = 0.f;   // [3][NT][8]: unused warp slots stay 0
+    if constexpr (BWD) {
+      for (int k = 0; k < 8; ++k) vc[k * NT + t] = 0.f;
+    } else {
+      for (int k = 0; k < 24; ++k) red1[t * 24 + k] = red2[t * 24 + k] = 0.f;   // [3][NT][8]: unused warp slots stay 0
+    }
   }
+  if (!BWD && threadIdx.x < 64) tailp[threadIdx.x] = 0.f;
   if (BWD && threadIdx.x == 32) {
-    float *bwc0 = reinterpret_cast<float *>(misc + 160);
-    int64_t *bwl0 = reinterpret_cast<int64_t *>(misc + 176);
+    float *bwc0 = reinterpret_cast<float *>(misc + 192);
+    int64_t *bwl0 = reinterpret_cast<int64_t *>(misc + 208);
     const int64_t gi = p.row_offset + i;
     const float ib = 1.f / (float)p.b_total;
     bwc0[0] = p.row_lse[i]; bwc0[1] = p.gscale[0] * ib; bwc0[2] = p.gscale[1] * ib; bwc0[3] = p.gscale[2];
@@ -313,7 +330,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   if (warp == MMA_WARP) tmem_alloc<512>(tmem_ptr);
   if (warp == TMA_WARP && lane == 0) {
-    prefetch_tmap(&tmQ); prefetch_tmap(&tmV); prefetch_tmap(&tmG);
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmV); prefetch_tmap(&tmG); prefetch_tmap(&tmGt);
     if constexpr (CL == 2) { prefetch_tmap(&tmV2); prefetch_tmap(&tmG2); }
   }
   fence_proxy_async_smem();           // the zero fill must be ordered before the TMA / MMA (async proxy) accesses
@@ -353,14 +370,24 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // same order as the MMA issuer consumes.  Forward, two S buffers: GEMM1 of the next image precedes GEMM2 (pass A of
       // the next pair runs inside the GEMM2 wait and needs S early).  Backward: GEMM2 first -- its Gx blocks are then
       // already in the ring when e2 is ready, and GEMM1 of the next image hides behind the two sweeps.
+      // the single-step tail block of Gx_j: own buffer, own barriers (every CTA fetches its own copy: 6 KB per pair)
+      const int nkb_ring = L.nkb_r - L.tail1;
+      auto load_tail = [&](int j) {
+        if (!L.tail1) return;
+        const int it = j - j0;
+        if (it > 0) mbar_spin(tail_empty, (it - 1) & 1);
+        mbar_arrive_expect_tx(tail_full, (uint32_t)L.rs * 32);
+        tma_load_3d(GT, &tmGt, tail_full, nkb_ring * 64, 0, j);
+      };
       if (nbuf == 2 && !BWD) {
         if (j0 < j1) load(&tmV, L.nkb_d, j0);
         for (int j = j0; j < j1; ++j) {
           if (j + 1 < j1) load(&tmV, L.nkb_d, j + 1);
-          load(&tmG, L.nkb_r, j);
+          load_tail(j);
+          load(&tmG, nkb_ring, j);
         }
       } else {
-        for (int j = j0; j < j1; ++j) { load(&tmV, L.nkb_d, j); load(&tmG, L.nkb_r, j); }
+        for (int j = j0; j < j1; ++j) { load(&tmV, L.nkb_d, j); load_tail(j); load(&tmG, nkb_ring, j); }
       }
     }
   } else if (warp == MMA_WARP) {
@@ -375,6 +402,8 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t dlo = (uint32_t)dproto;
       const uint32_t a_lo0 = dlo + (smem_u32(stages) >> 4), q_lo0 = dlo + (smem_u32(Qs) >> 4), e_lo0 = dlo + (smem_u32(E2) >> 4);
       const uint32_t stage_units = L.stage_bytes >> 4, kb_units = (uint32_t)(NT * 128) >> 4;
+      const uint64_t tproto = umma_desc_k_sw32(smem_u32(GT));
+      const uint32_t t_lo0 = (uint32_t)tproto, t_hi = (uint32_t)(tproto >> 32);
       const bool two_tiles = L.tiles == 2;
       auto gemm1 = [&](int it) {                       // S^T[buf] = vhat_j qhat_i^T
         const int b = it % nbuf, use = it / nbuf;
@@ -409,7 +438,8 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         TRACE(p, 0, it, 2);
         int left = L.k2_steps;
         const uint32_t dm = tmem_base + col_m;
-        for (int kb = 0; kb < L.nkb_r; ++kb) {
+        const int nkb_ring = L.nkb_r - L.tail1;
+        for (int kb = 0; kb < nkb_ring; ++kb) {
           mbar_spin(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_units, b_lo = e_lo0 + (uint32_t)kb * kb_units;
@@ -428,6 +458,16 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if constexpr (CL == 2) umma_commit_mc(&empty[stage], (uint16_t)3); else
           umma_commit(&empty[stage]);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (L.tail1) {                                   // last K = 16 step: A from the tail buffer (32-byte swizzle)
+          mbar_spin(tail_full, it & 1);
+          tc_fence_after();
+          const uint32_t b_lo = e_lo0 + (uint32_t)nkb_ring * kb_units;
+          if (!DBG(p, 64)) {
+            umma_f16_lohi2(dm, t_lo0, t_hi, b_lo, desc_hi, idesc, true);
+            if (two_tiles) umma_f16_lohi2(dm + NT, t_lo0 + ((128 * 32) >> 4), t_hi, b_lo, desc_hi, idesc, true);
+          }
+          umma_commit(tail_empty);
         }
         umma_commit(m_full);
         TRACE(p, 0, it, 3);
@@ -494,16 +534,15 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // The upstream gradients enter normalised by their larger magnitude, which is folded back into the GEMM / H
     // epilogue scale and into kq: the fp16 range of the scratch rows then does not depend on the loss weight
     // (LAMBDA = 50 in clip_coco_DMGAN.yml, an AMP loss scale of 2^16, ...)
-    float *bwc = reinterpret_cast<float *>(misc + 160);             // [0] row_lse, [1] g0/B, [2] g1/B, [3] |g| max
-    int64_t *bwl = reinterpret_cast<int64_t *>(misc + 176);         // [0] label of this row, [1] global row index
+    float *bwc = reinterpret_cast<float *>(misc + 192);             // [0] row_lse, [1] g0/B, [2] g1/B, [3] |g| max
+    int64_t *bwl = reinterpret_cast<int64_t *>(misc + 208);         // [0] label of this row, [1] global row index
     // ---- tail of the forward: per-word cosine (losses.py:197-198), gamma2 log-sum-exp (:199-203), statistics for the
     //      backward.  It runs one pair late, while GEMM2 of the next pair is in flight, and is SPREAD over the softmax warps
     //      (one lane per word): run by warp 0 alone, its ~2 k cycles made warp 0 the last to deliver e2 for every pair.
     //      |rho| <= 1 up to rounding, so the log-sum-exp uses the fixed shift gamma2 (the reference exponentiates without
     //      any shift); the warps' partial sums meet in shared memory and the last warp to arrive writes the score.  The
     //      bookkeeping is triple-buffered by pair index.
-    float *tailp = vc;                                              // [3][16] partial sums (vc is backward-only)
-    int *tailc = reinterpret_cast<int *>(vc + 48);                  // [3] arrival counters (zero-initialised with vc)
+    int *tailc = reinterpret_cast<int *>(tailp + 48);               // [3] arrival counters (zero-initialised)
     auto fwd_tail = [&](int it_, int j_) {
       const int rb_ = it_ % 3;
       mbar_wait(red_full, it_ & 1);
@@ -889,7 +928,8 @@ int make_map_f16(CUtensorMap *m, const void *base, uint64_t n0, uint64_t n1, uin
 
 // fp16 tensor (n2, n1, n0) with explicit box (b2, b1, b0 = 64), 128-byte swizzle
 int make_map_f16_box(CUtensorMap *m, const void *base, uint64_t n0, uint64_t n1, uint64_t n2, uint64_t pitch1_elems,
-                     uint64_t pitch2_elems, uint32_t box1, uint32_t box2, uint32_t box0 = 64, bool swizzle = true) {
+                     uint64_t pitch2_elems, uint32_t box1, uint32_t box2, uint32_t box0 = 64, bool swizzle = true,
+                     bool swizzle32 = false) {
   PFN_encodeTiled enc = get_encode();
   DAMSM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[3] = {n0, n1, n2};
@@ -897,7 +937,7 @@ int make_map_f16_box(CUtensorMap *m, const void *base, uint64_t n0, uint64_t n1,
   cuuint32_t box[3] = {box0, box1, box2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, !swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DAMSM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) dims=(%llu,%llu,%llu) box=(..,%u,%u)", (int)r,
                 (unsigned long long)n0, (unsigned long long)n1, (unsigned long long)n2, box1, box2);
@@ -929,6 +969,7 @@ struct TcLaunch {
   int nt;
   TcLayout L;
   CUtensorMap tmQ, tmV, tmG, tmV2, tmG2, tmVh, tmGh;   // full-row boxes; cluster mode: second / first half-row boxes
+  CUtensorMap tmGt;                                    // 16-column tail block of Gx (32-byte swizzle)
   TcStoreMaps tmS;                                     // backward: store maps of the e2 / dS scratch of the current chunk
   int sms;
   bool cluster_ok;
@@ -953,6 +994,10 @@ static int tc_prepare(TcLaunch *tl, const char *who, const void *qhat16, int64_t
   if ((rc = make_map_f16(&tl->tmQ, qhat16, d, q_rows, br, d, q_rows * d, tl->nt))) return rc;
   if ((rc = make_map_f16(&tl->tmV, vhat16, d, r, bc, d, r * d, tl->L.rs))) return rc;
   if ((rc = make_map_f16(&tl->tmG, gx, rk, r + 1, bc, rk, (r + 1) * rk, tl->L.rs))) return rc;
+  tl->tmGt = tl->tmG;
+  if (tl->L.tail1 &&
+      (rc = make_map_f16_box(&tl->tmGt, gx, rk, r + 1, bc, rk, (r + 1) * rk, (uint32_t)tl->L.rs, 1, 16, true, true)))
+    return rc;
   // cluster mode (pairs of captions share the image stream): half-row boxes for the two CTAs of a cluster
   tl->tmV2 = tl->tmV; tl->tmG2 = tl->tmG; for (int v = 0; v < 8; ++v) tl->tmS.e[v] = tl->tmS.d[v] = tl->tmQ;
   tl->cluster_ok = tl->nt == 80 && tl->L.act_warps <= 14 && tl->L.rs - tl->L.rs_half >= 8 && !getenv("DAMSM_TC_NO_CLUSTER");
@@ -997,11 +1042,11 @@ static int tc_launch(const TcLaunch &tl, TcParams &p, int64_t rows, cudaStream_t
     if (tl.L.act_warps <= 14) {                                                                                       \
       DAMSM_CUDA(cudaFuncSetAttribute(words_tc_kernel<NT_, BWD, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)tl.L.total));                                                              \
-      words_tc_kernel<NT_, BWD, 16, 1><<<grid, 16 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, tl.tmV, tl.tmG, tl.tmS, p); \
+      words_tc_kernel<NT_, BWD, 16, 1><<<grid, 16 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, tl.tmV, tl.tmG, tl.tmGt, tl.tmS, p); \
     } else {                                                                                                          \
       DAMSM_CUDA(cudaFuncSetAttribute(words_tc_kernel<NT_, BWD, 18, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)tl.L.total));                                                              \
-      words_tc_kernel<NT_, BWD, 18, 1><<<grid, 18 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, tl.tmV, tl.tmG, tl.tmS, p); \
+      words_tc_kernel<NT_, BWD, 18, 1><<<grid, 18 * 32, tl.L.total, st>>>(tl.tmQ, tl.tmV, tl.tmG, tl.tmV, tl.tmG, tl.tmGt, tl.tmS, p); \
     }                                                                                                                 \
   } while (0)
   // forward: always when possible; backward: opt-in (DAMSM_TC_CLUSTER_BWD=1) -- its kernel is bound by the softmax
@@ -1016,7 +1061,7 @@ static int tc_launch(const TcLaunch &tl, TcParams &p, int64_t rows, cudaStream_t
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    DAMSM_CUDA(cudaLaunchKernelEx(&cfg, kern, tl.tmQ, tl.tmVh, tl.tmGh, tl.tmV2, tl.tmG2, tl.tmS, p));
+    DAMSM_CUDA(cudaLaunchKernelEx(&cfg, kern, tl.tmQ, tl.tmVh, tl.tmGh, tl.tmV2, tl.tmG2, tl.tmGt, tl.tmS, p));
     return check_launch(BWD ? "words_bwd_tc (fused recompute, 2-CTA clusters)" : "words_fwd_tc (2-CTA clusters)");
   }
   switch (tl.nt) {
