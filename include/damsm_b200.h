@@ -215,6 +215,23 @@ DAMSM_API int damsm_cos_logits_bwd_f32(const float *a, int64_t lda, const float 
                              int64_t br, int64_t bc, int64_t d, float gamma3, float eps,
                              float *work, float *da, float *db, void *stream);
 
+/* ---- sentence-level matching loss as ONE launch each way (losses.py:51-91: the cosine logits :74-79, the class_ids mask
+ * :55-66,84 and the row / column soft-max statistics of both cross-entropies :87-88).  |logit| <= gamma3, so no running
+ * maximum is kept: usable for 0 <= gamma3 <= 60 (damsm_sent_fused_ok); the unfused entry points above serve the rest.
+ * forward: logits (br,bc) written masked and scaled, na (br), nb (bc) norms, row_lse (br) complete, col_max (bc) = 0 and
+ * col_sum (bc) = this block's sum exp(logit) (the partial form of damsm_ce_stats_f32; accumulated with atomics). */
+DAMSM_API int damsm_sent_fused_ok(float gamma3);
+DAMSM_API int damsm_sent_fwd_fused_f32(const float *a, int64_t lda, const float *b, int64_t ldb, const int64_t *cls_rows,
+                             const int64_t *cls_cols, int64_t row_offset, int64_t br, int64_t bc, int64_t d,
+                             float gamma3, float eps, float *logits, float *na, float *nb, float *row_lse,
+                             float *col_max, float *col_sum, void *stream);
+/* backward incl. both CEs (dL/dlogit rebuilt per tile from logits, row_lse, col_lse): da (br,d), db (bc,d) OVERWRITTEN */
+DAMSM_API int damsm_sent_bwd_fused_f32(const float *a, int64_t lda, const float *b, int64_t ldb, const float *na,
+                             const float *nb, const float *logits, const float *row_lse, const float *col_lse,
+                             const int64_t *labels, const float *gscale, int64_t row_offset, int64_t b_total,
+                             int64_t br, int64_t bc, int64_t d, float gamma3, float eps, float *da, float *db,
+                             void *stream);
+
 /* ---- NT-Xent contrastive term (nt_xent.py:16-35 with the mask of masks.py:3-17; used at
  * pretrain_DAMSM.py:170-174 and trainer.py:417-430).  z (n2,d) = cat(z_i, z_j), rows ldz floats apart, n2 = 2B.
  * sim (n2,n2) out: cosine / temperature, -inf on the diagonal; nrm (n2) = |z_a|; row_lse (n2);

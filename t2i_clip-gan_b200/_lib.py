@@ -48,6 +48,9 @@ SIGNATURES = {
     "damsm_cos_logits_f32": [_p, _l, _p, _l, _l, _l, _l, _f, _f, _p, _p, _p, _p],
     "damsm_cos_logits_bwd_f32": [_p, _l, _p, _l, _p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _l, _f, _f,
                                  _p, _p, _p, _p],
+    "damsm_sent_fused_ok": [_f],
+    "damsm_sent_fwd_fused_f32": [_p, _l, _p, _l, _p, _p, _l, _l, _l, _l, _f, _f, _p, _p, _p, _p, _p, _p, _p],
+    "damsm_sent_bwd_fused_f32": [_p, _l, _p, _l, _p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _l, _f, _f, _p, _p, _p],
     "damsm_ntxent_fwd_f32": [_p, _l, _l, _l, _f, _f, _p, _p, _p, _p, _p],
     "damsm_ntxent_bwd_f32": [_p, _l, _l, _l, _f, _f, _p, _p, _p, _p, _p, _p, _p],
     "damsm_rprecision_f32": [_p, _l, _p, _l, _l, _l, _l, _l, _f, _p, _p, _p],
@@ -69,6 +72,7 @@ LAUNCHES = {
     "damsm_resize_nearest_fwd": 1, "damsm_resize_nearest_bwd": 1, "damsm_gemm_tc": 1, "damsm_gram_pack_tc": 1, "damsm_words_tc_plan": 1, "damsm_words_fwd_tc": 1, "damsm_words_bwd_tc": 2,
     "damsm_pad_terms_fwd": 2, "damsm_ce_stats_f32": 2, "damsm_ce_losses_f32": 1,
     "damsm_cos_logits_f32": 4, "damsm_cos_logits_bwd_f32": 5,
+    "damsm_sent_fwd_fused_f32": 1, "damsm_sent_bwd_fused_f32": 1,
     "damsm_ntxent_fwd_f32": 3, "damsm_ntxent_bwd_f32": 4,
     "damsm_rm_special_token_fwd": 1, "damsm_rm_special_token_bwd": 1,
     "damsm_project_regions_fwd": 1, "damsm_project_regions_bwd": 1, "damsm_rprecision_f32": 1,

@@ -394,6 +394,39 @@ class CudaEngine(metaclass=_EngineMeta):
                   float(gamma3), float(eps), work.data_ptr(), da.data_ptr(), db.data_ptr(), _stream())
         return da, db
 
+    # ---- sentence loss, one launch each way (sent_fused.cu) -------------------------------------------------------
+    def sent_fused_ok(self, gamma3):
+        return bool(_lib.load().damsm_sent_fused_ok(float(gamma3)))
+
+    def sent_fwd(self, a, b, cls_rows, cls_cols, row_offset, gamma3, eps):
+        """Cosine logits + class mask + row LSE + column partials in ONE kernel.  Returns (logits, na, nb, row_lse,
+        col_max, col_sum) with (col_max, col_sum) in the partial form of ce_stats (col_max = 0)."""
+        _require_cuda(a, b, cls_rows, cls_cols)
+        br, d = a.shape
+        bc = b.shape[0]
+        dev = a.device
+        logits = torch.empty((br, bc), device=dev, dtype=torch.float32)
+        na = torch.empty(br, device=dev, dtype=torch.float32)
+        nb = torch.empty(bc, device=dev, dtype=torch.float32)
+        row_lse = torch.empty(br, device=dev, dtype=torch.float32)
+        col_max = torch.empty(bc, device=dev, dtype=torch.float32)
+        col_sum = torch.empty(bc, device=dev, dtype=torch.float32)
+        _lib.call("damsm_sent_fwd_fused_f32", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), _lib.ptr(cls_rows),
+                  _lib.ptr(cls_cols), int(row_offset), br, bc, d, float(gamma3), float(eps), logits.data_ptr(),
+                  na.data_ptr(), nb.data_ptr(), row_lse.data_ptr(), col_max.data_ptr(), col_sum.data_ptr(), _stream())
+        return logits, na, nb, row_lse, col_max, col_sum
+
+    def sent_bwd(self, a, b, na, nb, logits, row_lse, col_lse, labels, gscale, row_offset, b_total, gamma3, eps):
+        br, d = a.shape
+        bc = b.shape[0]
+        da = torch.empty((br, d), device=a.device, dtype=torch.float32)
+        db = torch.empty((bc, d), device=a.device, dtype=torch.float32)
+        _lib.call("damsm_sent_bwd_fused_f32", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), na.data_ptr(),
+                  nb.data_ptr(), logits.data_ptr(), row_lse.data_ptr(), col_lse.data_ptr(), _lib.ptr(labels),
+                  gscale.data_ptr(), int(row_offset), int(b_total), br, bc, d, float(gamma3), float(eps),
+                  da.data_ptr(), db.data_ptr(), _stream())
+        return da, db
+
     # ---- NT-Xent (nt_xent.py) -------------------------------------------------------------------------------
     def ntxent_fwd(self, z, inv_temp, eps):
         _require_cuda(z)

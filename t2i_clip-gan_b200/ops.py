@@ -300,13 +300,18 @@ class DamsmSentLoss(torch.autograd.Function):
         img = img.contiguous()
         txt_all = _all_gather_rows(txt.contiguous(), group)
         cls_all = _all_gather_rows(cls_local, group) if cls_local is not None else None
-        logits, na, nb = engine.cos_logits(img, txt_all, gamma3, eps)
-        row_lse, col_max, col_sum = engine.ce_stats(logits, cls_local, cls_all, row_offset)
+        fused = hasattr(engine, "sent_fwd") and engine.sent_fused_ok(gamma3)
+        if fused:                                # one launch: norms + logits + class mask + row LSE + column partials
+            logits, na, nb, row_lse, col_max, col_sum = engine.sent_fwd(img, txt_all, cls_local, cls_all, row_offset,
+                                                                        gamma3, eps)
+        else:
+            logits, na, nb = engine.cos_logits(img, txt_all, gamma3, eps)
+            row_lse, col_max, col_sum = engine.ce_stats(logits, cls_local, cls_all, row_offset)
         col_lse = combine_column_lse(col_max, col_sum, group)
         out2 = engine.ce_losses(logits, row_lse, col_lse, labels, row_offset, b_total)
         if group is not None:
             dist.all_reduce(out2, group=group)
-        ctx.engine, ctx.group, ctx.gamma3, ctx.eps = engine, group, gamma3, eps
+        ctx.engine, ctx.group, ctx.gamma3, ctx.eps, ctx.fused = engine, group, gamma3, eps, fused
         ctx.row_offset, ctx.b_total = row_offset, b_total
         ctx.save_for_backward(img, txt_all, labels, na, nb, logits, row_lse, col_lse)
         return out2[0].clone(), out2[1].clone()
@@ -315,8 +320,9 @@ class DamsmSentLoss(torch.autograd.Function):
     def backward(ctx, g0, g1):
         img, txt_all, labels, na, nb, logits, row_lse, col_lse = ctx.saved_tensors
         gscale = torch.stack([g0.reshape(()), g1.reshape(())]).to(torch.float32)
-        da, db = ctx.engine.cos_logits_bwd(img, txt_all, na, nb, logits, row_lse, col_lse, labels, gscale,
-                                           ctx.row_offset, ctx.b_total, ctx.gamma3, ctx.eps)
+        bwd = ctx.engine.sent_bwd if ctx.fused else ctx.engine.cos_logits_bwd
+        da, db = bwd(img, txt_all, na, nb, logits, row_lse, col_lse, labels, gscale,
+                     ctx.row_offset, ctx.b_total, ctx.gamma3, ctx.eps)
         dtxt = _reduce_scatter_rows(db, ctx.group) if ctx.needs_input_grad[1] else None
         return (da if ctx.needs_input_grad[0] else None), dtxt, None, None, None, None, None, None
 
