@@ -55,9 +55,10 @@ def emit(line):
 
 GAMMAS = (4.0, 5.0, 10.0)
 D = 512
-# DRAM bytes per scored pair of the word-loss launches (ncu --set full at B=592, U[T/3,T] caption lengths: forward 3.5 KB,
-# fused backward 56.5 KB, the two gradient GEMMs 49.4 KB, the H kernel 23.8 KB), profiles/r2_ncu_summary.md section 3
-TRAFFIC_BYTES_PER_PAIR = 3.5e3 + 56.5e3 + 49.4e3 + 23.8e3
+# DRAM bytes per scored pair of the word-loss launches (ncu --set full at B=592, U[T/3,T] caption lengths, 350,464 pairs:
+# forward 3.1 KB, fused backward 58.8 KB (TMA stores of the dS tile and of the e2 operand, 128-byte image pitch), the two
+# gradient GEMMs 50.2 KB, the H kernel 30.8 KB; profiles/r2_ncu_summary.md section 6)
+TRAFFIC_BYTES_PER_PAIR = 3.1e3 + 58.8e3 + 50.2e3 + 30.8e3
 # BASELINE.json configs[0..4]
 WORKLOADS = {
     "c1": dict(B=48, T=18, R=49, cls=True, precision="fp32", seed=2026, desc="CUB bird DAMSM shape"),
