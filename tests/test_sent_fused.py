@@ -10,6 +10,7 @@ from oracle import damsm_oracle as O
 
 pytestmark = pytest.mark.gpu
 pkg = importlib.import_module("t2i_clip-gan_b200")
+ops = importlib.import_module("t2i_clip-gan_b200.ops")
 TOL = 1e-5
 
 
@@ -28,7 +29,8 @@ def inputs(b, d, seed, n_classes):
 
 @pytest.mark.parametrize("b,d,n_classes,seed", [(48, 512, 200, 1), (10, 512, 0, 2), (130, 100, 5, 3), (65, 33, 3, 4),
                                                 (1, 16, 0, 5), (300, 256, 40, 6)])
-def test_fused_sentence_loss_vs_oracle(b, d, n_classes, seed):
+def test_fused_sentence_loss_vs_oracle(b, d, n_classes, seed, monkeypatch):
+    monkeypatch.setattr(ops, "SENT_FUSED_MAX_PAIRS", 1 << 40)      # the one-launch kernels at every size of this test
     img, txt, cls = inputs(b, d, seed, n_classes)
     labels = np.arange(b)
     o = O.sent_loss(img, txt, labels, cls, 10.0, g0=1.0, g1=0.7)
@@ -72,6 +74,21 @@ def test_fused_matches_unfused_block_and_zero_norm():
     assert rel(da.cpu().numpy(), da2.cpu().numpy()) <= 1e-5
     assert rel(db.cpu().numpy(), db2.cpu().numpy()) <= 1e-5
     assert torch.isfinite(da).all() and torch.isfinite(db).all()
+
+
+def test_size_dispatch():
+    """Up to SENT_FUSED_MAX_PAIRS logits the loss is 3 launches; larger batches take the tiled unfused kernels."""
+    for b, fused in ((48, True), (128, True), (160, False)):
+        img, txt, _ = inputs(b, 64, 9, 0)
+        ti = torch.tensor(img, device="cuda", requires_grad=True)
+        tt = torch.tensor(txt, device="cuda", requires_grad=True)
+        pkg._lib.reset_launch_count()
+        l0, l1 = pkg.sent_loss(ti, tt, torch.arange(b, device="cuda"), None, b)
+        (l0 + l1).backward()
+        assert (pkg._lib.launch_count() == 3) == fused
+        o = O.sent_loss(img, txt, np.arange(b), None, 10.0)
+        assert abs(l0.item() - o["loss0"]) <= TOL * max(1.0, abs(o["loss0"]))
+        assert rel(ti.grad.cpu().numpy(), o["dimg"]) <= TOL
 
 
 def test_large_gamma3_uses_the_unfused_path():
