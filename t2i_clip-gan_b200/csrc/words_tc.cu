@@ -513,13 +513,13 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t rowmask = valid ? 0xffffffffu : 0u;
     const bool k_row = rg < L.k2_steps * 16;                        // row lies inside GEMM2's K range
     const int e_warp = min(3, L.act_warps / 2 - 1);                 // backward: the warp whose lane 0 issues the e2 stores
-    // shared-memory address of e2[t = c0][r' = rg] and the 8 swizzle variants (t & 7)
-    uint32_t e2a[8];
-    {
-      const uint32_t base = smem_u32(E2) + (uint32_t)(rg >> 6) * (NT * 128) + (uint32_t)c0 * 128 + ((rg & 7) << 1);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) e2a[k] = base + (((((uint32_t)rg & 63) >> 3) ^ k) << 4);
-    }
+    // shared-memory address of e2[t = c0][r' = rg] INCLUDING the swizzle chunk of a word with (t & 7) == 0; word c0 + tl
+    // (c0 is a multiple of 8) lives at (e2base ^ ((tl & 7) << 4)) + tl * 128: bits 4-6 of the address carry only the
+    // 16-byte chunk index, so the swizzle is one XOR with a compile-time constant (eight precomputed addresses were
+    // rematerialised from %tid in every iteration once the register budget got tight: 508 instead of 210 instructions)
+    uint32_t e2base = smem_u32(E2) + (uint32_t)(rg >> 6) * (NT * 128) + (uint32_t)c0 * 128 + ((rg & 7) << 1) +
+                      ((((uint32_t)rg & 63) >> 3) << 4);
+    asm volatile("" : "+r"(e2base));                                // opaque: held in a register, not recomputed from %tid
     const float4 *tb4 = reinterpret_cast<const float4 *>(tb + c0);
     const float2 *tb22 = reinterpret_cast<const float2 *>(tb2 + c0);
     // cross-warp partial sums, laid out [parity][word t][8 warps of that word's half] so the tail reads float4s
@@ -706,8 +706,8 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t h2 = pack_half2(ex2f(ar.x), ex2f(ar.y)) & rowmask;   // rows >= R contribute nothing
         e2p[tl >> 1] = h2;
         if (k_row) {
-          sts_u16(e2a[tl & 7] + tl * 128, h2 & 0xffffu);
-          sts_u16(e2a[(tl + 1) & 7] + (tl + 1) * 128, h2 >> 16);
+          sts_u16((e2base ^ ((tl & 7) << 4)) + tl * 128, h2 & 0xffffu);
+          sts_u16((e2base ^ (((tl + 1) & 7) << 4)) + (tl + 1) * 128, h2 >> 16);
         }
       }
       // B2 (forward only, runs while GEMM2 is in flight): N' = sum_r e2 S partial sums
