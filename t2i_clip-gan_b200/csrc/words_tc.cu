@@ -132,6 +132,13 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Approximate (2 ulp) division / square root for the per-word scalars of the tail and coefficient steps: the IEEE
+// sequences are ~10 instructions each with a slow path, on code every softmax warp runs once per pair.
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
 }
@@ -556,9 +563,9 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float4 a0 = r1[2 * t], a1 = r1[2 * t + 1], b0 = r2[2 * t], b1 = r2[2 * t + 1];
         const float np = ((a0.x + a0.y) + (a0.z + a0.w)) + ((a1.x + a1.y) + (a1.z + a1.w));
         const float nn = ((b0.x + b0.y) + (b0.z + b0.w)) + ((b1.x + b1.y) + (b1.z + b1.w));
-        const float iy = 1.f / vYb_[t];
-        const float n = sqrtf(fmaxf(nn, 0.f)) * iy;
-        const float rho = (np * iy) / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
+        const float iy = __fdividef(1.f, vYb_[t]);
+        const float n = fast_sqrt(fmaxf(nn, 0.f)) * iy;
+        const float rho = __fdividef(np * iy, fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
         if (p.stats) {
           float *st = p.stats + pair * 3 * T;
           st[t] = rho; st[T + t] = n; st[2 * T + t] = iy;
@@ -650,8 +657,8 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (in) {
         const float omega = __expf(p.g2 * rho - lse);
         const float beta = g * p.g3 * omega;                                  // dL/drho_t
-        const float a = beta / (fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
-        bq = (n > kCosEps) ? beta * rho / (n * n) : 0.f;
+        const float a = __fdividef(beta, fmaxf(n, kCosEps) * fmaxf(vu[t], kCosEps));
+        bq = (n > kCosEps) ? __fdividef(beta * rho, n * n) : 0.f;
         vcb_[t] = p.scale_ds * p.g1 * a * iy;                                 // sp * cx
         vcb_[NT + t] = -p.scale_ds * p.g1 * bq * iy * iy;                     // -sp * cy
         vcb_[2 * NT + t] = a * iy * p.scale_ds;                               // cz
@@ -699,15 +706,18 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       TRACEW(p, it, 3);
 #pragma unroll
-      for (int tl = 0; tl < NH; tl += 2) {
+      for (int c = 0; c < NH / 8; ++c) {                             // nh is a multiple of 8: one length test per 8 words
         if (DBG(p, 32)) break;
-        if (tl >= nh) break;
-        const float2 ar = f2fma(make_float2(e1[tl], e1[tl + 1]), f2(k2), tb22[tl >> 1]);
-        const uint32_t h2 = pack_half2(ex2f(ar.x), ex2f(ar.y)) & rowmask;   // rows >= R contribute nothing
-        e2p[tl >> 1] = h2;
-        if (k_row) {
-          sts_u16((e2base ^ ((tl & 7) << 4)) + tl * 128, h2 & 0xffffu);
-          sts_u16((e2base ^ (((tl + 1) & 7) << 4)) + (tl + 1) * 128, h2 >> 16);
+        if (c * 8 >= nh) break;
+#pragma unroll
+        for (int tl = c * 8; tl < c * 8 + 8; tl += 2) {
+          const float2 ar = f2fma(make_float2(e1[tl], e1[tl + 1]), f2(k2), tb22[tl >> 1]);
+          const uint32_t h2 = pack_half2(ex2f(ar.x), ex2f(ar.y)) & rowmask;   // rows >= R contribute nothing
+          e2p[tl >> 1] = h2;
+          if (k_row) {
+            sts_u16((e2base ^ ((tl & 7) << 4)) + tl * 128, h2 & 0xffffu);
+            sts_u16((e2base ^ (((tl + 1) & 7) << 4)) + (tl + 1) * 128, h2 >> 16);
+          }
         }
       }
       // B2 (forward only, runs while GEMM2 is in flight): N' = sum_r e2 S partial sums
@@ -734,10 +744,13 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (lane == 0) mbar_arrive(e2_ready);
       if constexpr (BWD) {                                          // behind the arrival: GEMM2 does not need it
 #pragma unroll
-        for (int k = 0; k < NH / 2; ++k) {
-          if (2 * k >= nh) break;
-          const float2 pq = f2mul(make_float2(e1[2 * k], e1[2 * k + 1]), f2(invZ));
-          e1h[k] = pack_half2(pq.x, pq.y);
+        for (int c = 0; c < NH / 8; ++c) {
+          if (c * 8 >= nh) break;
+#pragma unroll
+          for (int k = c * 4; k < c * 4 + 4; ++k) {
+            const float2 pq = f2mul(make_float2(e1[2 * k], e1[2 * k + 1]), f2(invZ));
+            e1h[k] = pack_half2(pq.x, pq.y);
+          }
         }
       }
       if constexpr (!BWD) {
