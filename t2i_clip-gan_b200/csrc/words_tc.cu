@@ -268,8 +268,10 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t *bars = reinterpret_cast<uint64_t *>(misc);
   uint64_t *full = bars, *empty = bars + TC_STAGES;
   uint64_t *q_full = bars + 2 * TC_STAGES;            // 6
-  uint64_t *s_full = q_full + 1;                      // 7,8   (one per S buffer)
-  uint64_t *s_free = q_full + 3;                      // 9,10
+  // one s_full / s_free barrier per S buffer: 7,8 / 9,10 and, for the backward's third buffer, 22 / 23
+  constexpr bool NB3 = BWD && NT <= 64;               // 4 * tiles * NT <= 512 TMEM columns for either tile count
+  auto s_full = [&](int b) -> uint64_t * { if constexpr (NB3) return b < 2 ? q_full + 1 + b : bars + 22; else return q_full + 1 + b; };
+  auto s_free = [&](int b) -> uint64_t * { if constexpr (NB3) return b < 2 ? q_full + 3 + b : bars + 23; else return q_full + 3 + b; };
   uint64_t *e2_ready = q_full + 5, *m_full = q_full + 6, *m_free = q_full + 7;   // 11,12,13
   uint64_t *red_full = q_full + 8;                                               // 14 (forward: reductions published)
   uint64_t *coef_full = q_full + 8;                                              // 14,15 (backward: coefficients of even / odd pairs published)
@@ -297,7 +299,10 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int j0 = blockIdx.y * p.img_per_cta;
   const int j1 = min(p.bc, j0 + p.img_per_cta);
   const int T = p.T, R = p.R;
-  const int nbuf = L.nbuf;
+  // Backward: a THIRD S accumulator where TMEM has room (the NT <= 64 instances: 4 * tiles * NT <= 512 columns).  GEMM1 then runs two pairs ahead, right behind GEMM2 of the current pair, so S of the next pair is always
+  // complete when the softmax warps get to it (with two buffers GEMM1 of the next pair -- 64 MMAs -- only starts after
+  // GEMM2 and is not finished when the sweeps of a short caption are: 7 % of the warp samples sat on that s_full wait).
+  const int nbuf = NB3 ? 3 : L.nbuf;
 
   // operand rows past `rs` are read by the MMAs (ignored lanes): make every byte a finite fp16
   for (uint32_t o = threadIdx.x * 16; o < L.misc_off; o += TC_THREADS * 16)
@@ -305,10 +310,10 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
     mbar_init(tail_full, 1); mbar_init(tail_empty, 1);
-    mbar_init(q_full, 1); mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(m_full, 1);
+    mbar_init(q_full, 1); mbar_init(s_full(0), 1); mbar_init(s_full(1), 1); mbar_init(bars + 22, 1); mbar_init(m_full, 1);
     // the softmax warps arrive once per warp (lane 0 after __syncwarp): 448 per-thread arrivals on one shared-memory
     // word serialise and were the longest item of the per-pair critical path
-    mbar_init(&s_free[0], L.act_warps); mbar_init(&s_free[1], L.act_warps);
+    mbar_init(s_free(0), L.act_warps); mbar_init(s_free(1), L.act_warps); mbar_init(bars + 23, L.act_warps);
     mbar_init(e2_ready, L.act_warps); mbar_init(m_free, L.act_warps);
     if constexpr (BWD) { mbar_init(&coef_full[0], L.act_warps); mbar_init(&coef_full[1], L.act_warps); mbar_init(e2_free, 1);
                          mbar_init(ds_ready, L.act_warps); mbar_init(ds_free, 1); }
@@ -394,7 +399,15 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           load(&tmG, nkb_ring, j);
         }
       } else {
-        for (int j = j0; j < j1; ++j) { load(&tmV, L.nkb_d, j); load_tail(j); load(&tmG, nkb_ring, j); }
+        // backward (and single-buffer forward): GEMM2-first order with GEMM1 running `d` = nbuf - 1 pairs ahead
+        const int d = nbuf - 1;
+        for (int k = 0; k < d && j0 + k < j1; ++k) load(&tmV, L.nkb_d, j0 + k);
+        for (int j = j0; j < j1; ++j) {
+          if (d == 0) load(&tmV, L.nkb_d, j);
+          load_tail(j);
+          load(&tmG, nkb_ring, j);
+          if (d > 0 && j + d < j1) load(&tmV, L.nkb_d, j + d);
+        }
       }
     }
   } else if (warp == MMA_WARP) {
@@ -414,7 +427,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const bool two_tiles = L.tiles == 2;
       auto gemm1 = [&](int it) {                       // S^T[buf] = vhat_j qhat_i^T
         const int b = it % nbuf, use = it / nbuf;
-        if (use > 0) mbar_spin(&s_free[b], (use - 1) & 1);
+        if (use > 0) mbar_spin(s_free(b), (use - 1) & 1);
         tc_fence_after();
         TRACE(p, 0, it, 0);
         const uint32_t d0 = tmem_base + (uint32_t)(b * L.tiles * NT);
@@ -435,7 +448,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           umma_commit(&empty[stage]);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&s_full[b]);
+        umma_commit(s_full(b));
         TRACE(p, 0, it, 1);
       };
       auto gemm2 = [&](int it) {                       // M'^T = Gx_j e2
@@ -500,10 +513,13 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           gemm2(it);
         }
       } else {
+        const int d = nbuf - 1;                                      // same order as the producer
+        for (int k = 0; k < d && k < n; ++k) gemm1(k);
         for (int it = 0; it < n; ++it) {
-          gemm1(it);
+          if (d == 0) gemm1(it);
           if (BWD && it > 0) dsstore(it - 1);
           gemm2(it);
+          if (d > 0 && it + d < n) gemm1(it + d);
         }
         if (BWD && n > 0) { dsstore(n - 1); bulk_wait_group0(); }
       }
@@ -595,7 +611,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     auto pass_a = [&](int it_) {
       const int b_ = it_ % nbuf;
       const uint32_t ts_ = t_lane + (uint32_t)(b_ * L.tiles * NT);
-      mbar_wait(&s_full[b_], (it_ / nbuf) & 1);
+      mbar_wait(s_full(b_), (it_ / nbuf) & 1);
       tc_fence_after();
       float2 zp2 = make_float2(0.f, 0.f);
       if (DBG(p, 32)) {
@@ -759,7 +775,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[b]);                     // forward: S is dead from here on
+        if (lane == 0) mbar_arrive(s_free(b));                      // forward: S is dead from here on
       }
       if constexpr (BWD) {
         // coefficients of the NEXT pair while GEMM2 of this one is in flight (see bwd_coef)
@@ -888,7 +904,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(ds_ready);
-          mbar_arrive(&s_free[b]);
+          mbar_arrive(s_free(b));
           mbar_arrive(m_free);
         }
       }
@@ -989,8 +1005,8 @@ struct TcLaunch {
 };
 
 static int tc_prepare(TcLaunch *tl, const char *who, const void *qhat16, int64_t q_rows, const void *vhat16,
-                      const void *gx, int64_t br, int64_t bc, int64_t t, int64_t r, int64_t d) {
-  tl->nt = pick_nt((int)t);
+                      const void *gx, int64_t br, int64_t bc, int64_t t, int64_t r, int64_t d, int nt_override = 0) {
+  tl->nt = nt_override > 0 ? nt_override : pick_nt((int)t);
   DAMSM_REQUIRE(tl->nt > 0, "%s: T=%lld outside [1,128]", who, (long long)t);
   DAMSM_REQUIRE(r >= 1 && r <= 255, "%s: R=%lld outside [1,255]", who, (long long)r);
   DAMSM_REQUIRE(d >= 64 && d % 64 == 0, "%s: D=%lld must be a multiple of 64", who, (long long)d);
@@ -1247,9 +1263,22 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
   if (br == 0 || bc == 0) return 0;
   DAMSM_REQUIRE(n_chunks >= 1 && chunk_pos_host[0] == 0 && chunk_pos_host[n_chunks] == br,
                 "words_bwd_tc: the chunk table must cover the sorted captions [0, br)");
-  TcLaunch tl;
+  // Caption-length groups: the kernel template is instantiated per column count NT, and a caption that computes nw <= 64
+  // (<= 32) word columns runs in the NT = 64 (32) instance: its S accumulators are small enough for a third TMEM buffer
+  // (GEMM1 two pairs ahead), its resident caption tile and e2 buffer are smaller.  Captions are sorted by nw, so the
+  // groups are contiguous ranges of every chunk.
+  int gnt[3], ng = 0;
+  {
+    const int nt_full = pick_nt((int)t);
+    const int cand[3] = {nt_full, 64, 32};
+    for (int c = 0; c < 3; ++c)
+      if (cand[c] > 0 && cand[c] <= nt_full && (ng == 0 || cand[c] < gnt[ng - 1])) gnt[ng++] = cand[c];
+  }
+  DAMSM_REQUIRE(ng >= 1, "words_bwd_tc: T=%lld outside [1,128]", (long long)t);
+  TcLaunch tls[3];
   int rc;
-  if ((rc = tc_prepare(&tl, "words_bwd_tc", qhat16, q_rows, vhat16, gx, br, bc, t, r, d))) return rc;
+  for (int g = 0; g < ng; ++g)
+    if ((rc = tc_prepare(&tls[g], "words_bwd_tc", qhat16, q_rows, vhat16, gx, br, bc, t, r, d, gnt[g]))) return rc;
   const int64_t col_bytes = damsm_words_bwd_tc_col_bytes(bc, r);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n_rows = bc * r;
@@ -1288,15 +1317,16 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
     p.i0 = (int)s0; p.kc = kc; p.row_lse = row_lse; p.col_lse = col_lse; p.gscale = scal;
     p.labels = labels; p.row_offset = row_offset; p.b_total = b_total; p.kq = kq;
     p.x_ds = x_ds; p.store_e = hmat ? 1 : 0; p.svec = svec; p.scale_ds = scale_ds; p.scale_e = scale_e;
-    for (int v = 0; v < tl.nt / 16; ++v) {
+    for (int v = 0; v < tls[0].nt / 16; ++v) {
       const uint32_t nwv = 16u * (v + 1);
-      if ((rc = make_map_f16_box(&tl.tmS.d[v], x_ds, (uint64_t)kc, (uint64_t)r, (uint64_t)bc, (uint64_t)kc, (uint64_t)(r * kc),
-                                 (uint32_t)((r + 7) / 8 * 8), 1, nwv, false)))
+      if ((rc = make_map_f16_box(&tls[0].tmS.d[v], x_ds, (uint64_t)kc, (uint64_t)r, (uint64_t)bc, (uint64_t)kc,
+                                 (uint64_t)(r * kc), (uint32_t)((r + 7) / 8 * 8), 1, nwv, false)))
         return rc;
-      if (hmat && (rc = make_map_f16_box(&tl.tmS.e[v], x_e, (uint64_t)rp, (uint64_t)bc, (uint64_t)kc, (uint64_t)rp,
+      if (hmat && (rc = make_map_f16_box(&tls[0].tmS.e[v], x_e, (uint64_t)rp, (uint64_t)bc, (uint64_t)kc, (uint64_t)rp,
                                          (uint64_t)(bc * rp), 1, nwv)))
         return rc;
     }
+    for (int g = 1; g < ng; ++g) tls[g].tmS = tls[0].tmS;          // the maps are indexed by nw / 16 - 1
 #ifdef DAMSM_TC_DEBUG
     p.dbg = getenv("DAMSM_DBG") ? atoi(getenv("DAMSM_DBG")) : 0;
 #endif
@@ -1310,7 +1340,22 @@ extern "C" int damsm_words_bwd_tc(const void *qhat16, int64_t q_rows, const void
       if (p.trace_block >= s1 - s0) p.trace_block = (int)(s1 - s0 - 1);
     }
 #endif
-    if ((rc = tc_launch<true>(tl, p, s1 - s0, st))) return rc;
+    {
+      // sorted positions [s0, s1): nw descending -> one launch per non-empty caption-length group
+      int64_t a = s0;
+      for (int g = 0; g < ng; ++g) {
+        const int64_t lower = g + 1 < ng ? gnt[g + 1] : 0;         // this group: lower < nw <= gnt[g]
+        int64_t b = a;
+        while (b < s1 && koff_host[b + 1] - koff_host[b] > lower) ++b;
+        if (b > a) {
+          DAMSM_REQUIRE(koff_host[a + 1] - koff_host[a] <= gnt[g], "words_bwd_tc: captions are not sorted by word count");
+          p.i0 = (int)a;
+          if ((rc = tc_launch<true>(tls[g], p, b - a, st))) return rc;
+        }
+        a = b;
+      }
+      DAMSM_REQUIRE(a == s1, "words_bwd_tc: captions are not sorted by word count");
+    }
 #ifdef DAMSM_TC_DEBUG
     if (getenv("DAMSM_TRACE_BWD")) {     // tools/trace_bwd.py: per-pair clock trace of one CTA
       long long h[3 * 16 * 8];

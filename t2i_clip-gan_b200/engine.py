@@ -304,7 +304,11 @@ class CudaEngine(metaclass=_EngineMeta):
                   qpack16.data_ptr(), _lib.ptr(dqpack), _lib.ptr(dvhat), _lib.ptr(hmat), kq.data_ptr(), _stream())
         # own kernels: scalars + packing (counted by the call) + per chunk the fused recompute, the dvhat GEMM and the
         # H kernel (image side), the dqhat GEMM (caption side)
-        _lib.add_launches((1 + (2 if need_dv else 0) + (1 if need_dq else 0)) * n_chunks)
+        # the fused kernel is launched once per caption-length group (nw <= 32, <= 64, longer) present in a chunk
+        nws = nw_host[order_host].astype(np.int64)
+        gid = (nws > 32).astype(np.int64) + (nws > 64)
+        n_fused = sum(len(np.unique(gid[chunk_pos[c]:chunk_pos[c + 1]])) for c in range(n_chunks))
+        _lib.add_launches(n_fused + ((2 if need_dv else 0) + (1 if need_dq else 0)) * n_chunks)
         # closed form of the skipped words + unpacking of the packed word-row gradients (pad_terms.cu)
         coef = dqpad = dvbar = scal = None
         if pad is not None:

@@ -19,6 +19,8 @@ def child(b, reps, lib):
     w = torch.randn(b, T, D, device="cuda", generator=g)
     r = torch.randn(b, R, D, device="cuda", generator=g)
     lens = torch.randint(T // 3, T + 1, (b,), device="cuda", generator=g)
+    if os.environ.get("AB_LEN"):                              # every caption has this many words
+        lens = torch.full((b,), int(os.environ["AB_LEN"]), device="cuda")
     m = (torch.arange(T, device="cuda")[None, :] < lens[:, None]).to(torch.uint8).contiguous()
     qhat, qhat16, _, qun = eng.l2norm_fwd(w, want_bf16=True, pad8=True)
     vhat, vhat16, _, _ = eng.l2norm_fwd(r, want_bf16=True)
@@ -40,6 +42,8 @@ def child(b, reps, lib):
     tf, _ = timed(lambda: eng.words_fwd(qhat, qhat16, vhat, col, qun, m, gam))
     tb, out = timed(lambda: eng.words_bwd(qhat, qhat16, vhat, col, qun, m, sim, row_lse, col_lse, None, gs, 0, b, gam))
     chk = [float(x.double().abs().sum()) for x in out if x is not None]
+    k = 1e-3 * 1.9e9 * 148 / (b * b)
+    print(f"[{tf * k:6.0f} / {tb * k:6.0f} clk per pair @1.9GHz] ", end="")
     print(f"{os.path.basename(lib):28s} B={b}: fwd {tf:8.3f} ms  bwd {tb:8.3f} ms  sum {tf + tb:8.3f}  "
           f"sim {float(sim.double().sum()):.6f} chk {' '.join(f'{c:.6e}' for c in chk)}", flush=True)
 
