@@ -28,7 +28,8 @@
 namespace damsm {
 using namespace tc;
 
-constexpr int TC_STAGES = 3;
+constexpr int TC_MIN_STAGES = 3, TC_MAX_STAGES = 6;   // operand ring depth: as many slots as shared memory holds
+constexpr uint32_t TC_SMEM_LIMIT = 232448;              // 227 KB of shared memory per CTA on sm_100
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct TcLayout {
@@ -39,6 +40,7 @@ struct TcLayout {
   int nkb_d, nkb_r;  // 64-wide k-blocks of GEMM1 / GEMM2
   int nbuf;          // S accumulators in TMEM (2 when 3*tiles*NT <= 512 columns)
   int act_warps;     // softmax warps that own at least one row below max(16*k2_steps, R+1)
+  int stages;        // operand ring slots: 3 with the NT = 80 caption tile at R = 196, more in the smaller instances
   int tail1;         // the last k-block of GEMM2 is a single K=16 step (R = 196: 13 steps): its Gx columns get a buffer of
                      // their own (32-byte rows, 32-byte swizzle) instead of a fourth slot-sized block through the 3-slot ring
   uint32_t q_bytes, stage_bytes, e2_bytes, tail_off, tail_bytes, misc_off, total;
@@ -63,14 +65,19 @@ __host__ __device__ inline TcLayout tc_layout(int NT, int R, int D) {
   // the overrun of the last stage may reach into the e2 buffer but not into the fp32 bookkeeping behind it.
   if ((uint32_t)l.tiles * 16384 > l.stage_bytes + l.e2_bytes) l.stage_bytes = (uint32_t)l.tiles * 16384;
   l.tail1 = (l.k2_steps % 4 == 1 && l.nkb_r > 1) ? 1 : 0;
-  l.tail_off = l.q_bytes + TC_STAGES * l.stage_bytes + l.e2_bytes;
   l.tail_bytes = l.tail1 ? (uint32_t)l.tiles * 128 * 32 : 0;       // all M rows of the MMAs: rows past `rs` stay zero
-  l.misc_off = l.tail_off + l.tail_bytes;
-  // misc: 256 B of barriers / scalars, then floats: u,tb,tb2 [NT] + zbuf [2][2][256] and
+  // misc: 512 B of barriers / scalars, then floats: u,tb,tb2 [NT] + zbuf [2][2][256] and
   //   forward:  Y [3][NT] + red1/red2 [3][NT][8] + tail partial sums [64]   ([3] = buffered by pair index, see fwd_tail)
   //   backward: coefficients [2][4][NT] + wbuf [2][2][256]
   const uint32_t fl_fwd = 3 * NT + 1024 + 3 * NT + 48 * NT + 64, fl_bwd = 3 * NT + 1024 + 8 * NT + 1024;
-  l.total = l.misc_off + 256 + 4 * (fl_fwd > fl_bwd ? fl_fwd : fl_bwd) + 1024 /*alignment slack*/;
+  const uint32_t misc_bytes = 512 + 4 * (fl_fwd > fl_bwd ? fl_fwd : fl_bwd) + 1024 /*alignment slack*/;
+  // the ring is paced by the slot turn-around (MMA consumption + commit + TMA latency ~ 2 k cycles per slot): every slot
+  // that fits is throughput for the pairs of short captions, whose softmax work no longer covers the operand stream
+  for (l.stages = TC_MAX_STAGES; l.stages > TC_MIN_STAGES; --l.stages)
+    if (l.q_bytes + (uint32_t)l.stages * l.stage_bytes + l.e2_bytes + l.tail_bytes + misc_bytes <= TC_SMEM_LIMIT) break;
+  l.tail_off = l.q_bytes + (uint32_t)l.stages * l.stage_bytes + l.e2_bytes;
+  l.misc_off = l.tail_off + l.tail_bytes;
+  l.total = l.misc_off + misc_bytes;
   return l;
 }
 
@@ -105,6 +112,8 @@ struct TcParams {
   const int *nw;       // (br) or NULL = every caption uses all NT columns
   const int *order;    // (br) caption processed by CTA row x (captions sorted by nw, longest first) or NULL = identity
   const float *epad;   // forward: (br, bc) sum over the skipped words of exp(gamma2 rho_bar), or NULL
+  int grp_lo, grp_hi;  // forward: this launch serves the captions with grp_lo < nw <= grp_hi (grp_hi == 0: all of them)
+  int grp_pair;        // forward: positions 2k, 2k+1 of the sorted order are grouped together, by the longer caption
   float *sim;          // forward: out (br, bc); backward: in (masked, gamma3-scaled)
   float *stats;        // (br, bc, 3, T): rho, ||c||, 1/Y per word; forward writes (may be NULL), backward reads
   // ---- backward only ----
@@ -263,11 +272,12 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const TcLayout L = tc_layout(NT, p.R, p.D);
   uint8_t *Qs = smem;
   uint8_t *stages = Qs + L.q_bytes;
-  uint8_t *E2 = stages + TC_STAGES * L.stage_bytes;
+  const int NS = L.stages;                            // operand ring slots
+  uint8_t *E2 = stages + NS * L.stage_bytes;
   uint8_t *misc = smem + L.misc_off;
   uint64_t *bars = reinterpret_cast<uint64_t *>(misc);
-  uint64_t *full = bars, *empty = bars + TC_STAGES;
-  uint64_t *q_full = bars + 2 * TC_STAGES;            // 6
+  uint64_t *full = bars + 32, *empty = bars + 32 + TC_MAX_STAGES;   // ring barriers: second half of the 512-byte header
+  uint64_t *q_full = bars + 6;
   // one s_full / s_free barrier per S buffer: 7,8 / 9,10 and, for the backward's third buffer, 22 / 23
   constexpr bool NB3 = BWD && NT <= 64;               // 4 * tiles * NT <= 512 TMEM columns for either tile count
   auto s_full = [&](int b) -> uint64_t * { if constexpr (NB3) return b < 2 ? q_full + 1 + b : bars + 22; else return q_full + 1 + b; };
@@ -278,7 +288,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 16);
   uint64_t *e2_free = bars + 17;                                                 // backward: the e2 operand has left the chip
   uint64_t *ds_ready = bars + 18, *ds_free = bars + 19;                          // backward: dS tile staged / stored
-  float *vu = reinterpret_cast<float *>(misc + 256);          // [NT] ||qhat_t||
+  float *vu = reinterpret_cast<float *>(misc + 512);          // [NT] ||qhat_t||
   float *tb = vu + NT;                                        // 0 for real words, -inf for padding and t >= T
   float *tb2 = tb + NT;                                       // 0 for t < T, -inf for t >= T
   float *zbuf = tb2 + NT;                                     // [2 parities][2 halves][256]
@@ -295,6 +305,20 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int spos = (BWD ? p.i0 : 0) + blockIdx.x;                  // position in the sorted caption order
   const int i = p.order ? p.order[spos] : spos;
   const int NTi = p.nw ? p.nw[i] : NT;                             // word columns this caption computes (multiple of 16)
+  if constexpr (!BWD) {
+    // Forward launches are per caption-length group over ALL caption rows (the word counts are only known on the
+    // device): a CTA whose caption belongs to another group leaves at once.  With an even number of rows the captions at
+    // positions 2k, 2k+1 go together, by the longer of the two (the two CTAs of a cluster must decide alike, and every
+    // launch -- clustered or not -- must apply the same rule).
+    if (p.nw && p.grp_hi > 0) {
+      int ng_ = NTi;
+      if (p.grp_pair) {
+        const int ip = p.order ? p.order[spos ^ 1] : (spos ^ 1);
+        ng_ = max(ng_, p.nw[ip]);
+      }
+      if (ng_ <= p.grp_lo || ng_ > p.grp_hi) return;
+    }
+  }
   const int nh = NTi >> 1;                                         // ... per softmax thread (multiple of 8)
   const int j0 = blockIdx.y * p.img_per_cta;
   const int j1 = min(p.bc, j0 + p.img_per_cta);
@@ -308,7 +332,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   for (uint32_t o = threadIdx.x * 16; o < L.misc_off; o += TC_THREADS * 16)
     *reinterpret_cast<uint4 *>(smem + o) = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
+    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
     mbar_init(tail_full, 1); mbar_init(tail_empty, 1);
     mbar_init(q_full, 1); mbar_init(s_full(0), 1); mbar_init(s_full(1), 1); mbar_init(bars + 22, 1); mbar_init(m_full, 1);
     // the softmax warps arrive once per warp (lane 0 after __syncwarp): 448 per-thread arrivals on one shared-memory
@@ -376,7 +400,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tma_load_3d(stages + stage * L.stage_bytes, m, &full[stage], kb * 64, 0, j);
           }
           }
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       };
       // same order as the MMA issuer consumes.  Forward, two S buffers: GEMM1 of the next image precedes GEMM2 (pass A of
@@ -446,7 +470,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (DBG(p, 128)) mbar_arrive(&empty[stage]); else
           if constexpr (CL == 2) umma_commit_mc(&empty[stage], (uint16_t)3); else
           umma_commit(&empty[stage]);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NS) { stage = 0; phase ^= 1; }
         }
         umma_commit(s_full(b));
         TRACE(p, 0, it, 1);
@@ -477,7 +501,7 @@ words_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (DBG(p, 128)) mbar_arrive(&empty[stage]); else
           if constexpr (CL == 2) umma_commit_mc(&empty[stage], (uint16_t)3); else
           umma_commit(&empty[stage]);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NS) { stage = 0; phase ^= 1; }
         }
         if (L.tail1) {                                   // last K = 16 step: A from the tail buffer (32-byte swizzle)
           mbar_spin(tail_full, it & 1);
@@ -1029,7 +1053,7 @@ static int tc_prepare(TcLaunch *tl, const char *who, const void *qhat16, int64_t
     return rc;
   // cluster mode (pairs of captions share the image stream): half-row boxes for the two CTAs of a cluster
   tl->tmV2 = tl->tmV; tl->tmG2 = tl->tmG; for (int v = 0; v < 8; ++v) tl->tmS.e[v] = tl->tmS.d[v] = tl->tmQ;
-  tl->cluster_ok = tl->nt == 80 && tl->L.act_warps <= 14 && tl->L.rs - tl->L.rs_half >= 8 && !getenv("DAMSM_TC_NO_CLUSTER");
+  tl->cluster_ok = tl->nt <= 80 && tl->L.act_warps <= 14 && tl->L.rs - tl->L.rs_half >= 8 && !getenv("DAMSM_TC_NO_CLUSTER");
   if (tl->cluster_ok) {
     CUtensorMap a, b;
     const uint32_t h0 = (uint32_t)tl->L.rs_half, h1 = (uint32_t)(tl->L.rs - tl->L.rs_half);
@@ -1082,7 +1106,8 @@ static int tc_launch(const TcLaunch &tl, TcParams &p, int64_t rows, cudaStream_t
   // warps, not by the image stream, and the lock-step of the two CTAs costs it ~1 % (measured at C5)
   if (tl.cluster_ok && rows % 2 == 0 && (!BWD || getenv("DAMSM_TC_CLUSTER_BWD"))) {
     // pairs of caption rows as 2-CTA clusters sharing the image stream by TMA multicast
-    auto kern = words_tc_kernel<80, BWD, 16, 2>;
+    auto kern = tl.nt == 32 ? words_tc_kernel<32, BWD, 16, 2> : tl.nt == 64 ? words_tc_kernel<64, BWD, 16, 2>
+                                                                            : words_tc_kernel<80, BWD, 16, 2>;
     DAMSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.L.total));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(16 * 32); cfg.dynamicSmemBytes = tl.L.total; cfg.stream = st;
@@ -1208,9 +1233,22 @@ extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void
                                   void *stream) {
   DAMSM_REQUIRE(qhat16 && vhat16 && gx && unorm && mask && sim, "words_fwd_tc: null pointer");
   if (br == 0 || bc == 0) return 0;
-  TcLaunch tl;
+  // caption-length groups as in the backward (see damsm_words_bwd_tc); without a plan (nw == NULL) one launch serves all
+  int gnt[3], ng = 0;
+  {
+    const int nt_full = pick_nt((int)t);
+    const int cand[3] = {nt_full, 64, 32};
+    for (int c = 0; c < 3; ++c)
+      if (cand[c] > 0 && cand[c] <= nt_full && (ng == 0 || cand[c] < gnt[ng - 1])) gnt[ng++] = cand[c];
+    if (!nw && ng > 1) ng = 1;
+  }
+  DAMSM_REQUIRE(ng >= 1, "words_fwd_tc: T=%lld outside [1,128]", (long long)t);
+  TcLaunch tls[3];
   int rc;
-  if ((rc = tc_prepare(&tl, "words_fwd_tc", qhat16, q_rows, vhat16, gx, br, bc, t, r, d))) return rc;
+  for (int g = 0; g < ng; ++g)
+    if ((rc = tc_prepare(&tls[g], "words_fwd_tc", qhat16, q_rows, vhat16, gx, br, bc, t, r, d, gnt[g]))) return rc;
+  TcLaunch &tl = tls[0];
+  (void)tl;
   TcParams p{};
   p.br = (int)br; p.bc = (int)bc; p.T = (int)t; p.R = (int)r; p.D = (int)d;
   p.g1 = gamma1; p.g2 = gamma2; p.g3 = gamma3; p.mask = mask; p.unorm = unorm; p.sim = sim; p.stats = stats;
@@ -1236,7 +1274,13 @@ extern "C" int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void
     return rc2;
   }
 #endif
-  return tc_launch<false>(tl, p, br, (cudaStream_t)stream);
+  p.grp_pair = (br % 2 == 0) ? 1 : 0;
+  for (int g = 0; g < ng; ++g) {
+    p.grp_lo = g + 1 < ng ? gnt[g + 1] : 0;
+    p.grp_hi = ng > 1 ? (g == 0 ? 1 << 30 : gnt[g]) : 0;
+    if ((rc = tc_launch<false>(tls[g], p, br, (cudaStream_t)stream))) return rc;
+  }
+  return 0;
 }
 
 extern "C" int64_t damsm_words_bwd_tc_fixed_bytes(void) { return TC_SCAL_BYTES; }

@@ -166,6 +166,7 @@ class CudaEngine(metaclass=_EngineMeta):
                       _lib.ptr(pad["epad"]) if pad else None, br, bc, t, r, d,
                       float(gammas[0]), float(gammas[1]), float(gammas[2]), sim.data_ptr(), _lib.ptr(stats),
                       _stream())
+            _lib.add_launches((t > 32) + (t > 64))        # one launch per caption-length group (nw <= 32, <= 64, longer)
         else:
             _lib.call("damsm_words_fwd_f32", qhat.data_ptr(), vhat.data_ptr(), col["gram"].data_ptr(),
                       unorm.data_ptr(), mask_u8.data_ptr(), br, bc, t, r, d,
