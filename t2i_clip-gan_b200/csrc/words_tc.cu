@@ -9,15 +9,21 @@
 //                                                                yields Y_t = sum_r e2 (softmax-over-regions denominator)
 //   regs   N'_t = sum_r e2 S, NN_t = sum_r e2 M'  (warp butterfly + shared memory across warps)
 //          rho_t = (N'/Y) / (max(sqrt(NN)/Y, eps) max(u_t, eps)),  sim = gamma3/gamma2 log sum_t exp(gamma2 rho_t)
-//   bwd    the same recompute, then dS = a A + P (dP - W), dP = gamma1 A (a S - b M), W = sum_t P dP; dS and A leave
-//          the chip as scaled fp16 rows that the own tcgen05 GEMM (gemm_tc.cu: dvhat, dqhat) and hmat_tc.cu (H) contract per chunk.
+//   bwd    the same recompute, then dS = a A + P (dP - W), dP = gamma1 A (a S - b M), W = sum_t P dP.  The two scratch
+//          tiles of a pair leave the chip by TMA store from shared memory: the fp16 e2 operand of GEMM2 itself (word-major
+//          x_e; the H kernel folds 1/Y^2 into its scales) and the scaled fp16 dS tile staged in the same buffer
+//          (region-major x_ds); the own tcgen05 GEMM (gemm_tc.cu: dvhat, dqhat) and hmat_tc.cu (H) contract them per chunk.
+//          Per-word coefficients are computed one pair ahead, spread over the softmax warps.
 //
 // Regions live on the MMA M axis (TMEM lanes): the softmax over words, its backward column term and every
 // per-region quantity are then thread-local, and the accumulators (NT columns per tile) leave TMEM room for a
 // second S buffer, so GEMM1 of the next image overlaps the register work of the current one.
 // Warp roles: 0-15 softmax/epilogue (TMEM lane quadrant = warp%4, tile = (warp/4)%2, word half = warp/8); the TMA
 // producer and the MMA issuer are warps 7 and 15 (which own no region row when R+1 <= 224) or two extra warps 16/17.
-// Forward launches pair the CTAs of two captions into a cluster that shares the image stream by TMA multicast.
+// Launches pair the CTAs of two captions into a cluster that shares the image stream by TMA multicast (forward; backward
+// opt-in).  The template is instantiated per column count NT: captions are sorted by their word count and every
+// caption-length group (nw <= 32, <= 64, longer) runs in the smallest instance that holds it -- deeper operand ring, and
+// in the backward a third S accumulator (GEMM1 two pairs ahead).
 // Budgets and the roofline are in DESIGN.md.
 #include <stdlib.h>
 #include <type_traits>
