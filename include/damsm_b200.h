@@ -138,21 +138,25 @@ DAMSM_API int damsm_words_tc_plan(const uint8_t *mask, int64_t br, int64_t t, in
  * stats (br, bc, 3, T) fp32 or NULL: per pair and word the cosine rho_t, ||c_t|| and 1/Y_t that the backward
  * needs (12*T bytes per pair; B^2*T, not B^2*T*R; only words t < nw[i] are written).
  * nw / order (damsm_words_tc_plan) and epad (br, bc) = sum over the skipped words of exp(gamma2 rho_bar)
- * (damsm_pad_terms_fwd) may all be NULL: every caption then computes all its words. */
+ * (damsm_pad_terms_fwd) may all be NULL: every caption then computes all its words.  With a plan the kernel is launched
+ * once per caption-length group (nw <= 32, <= 64, longer; every launch covers all rows and a CTA of another group
+ * leaves at once). */
 DAMSM_API int damsm_words_fwd_tc(const void *qhat16, int64_t q_rows, const void *vhat16, const void *gx,
                                  const float *unorm, const uint8_t *mask, const int32_t *nw, const int32_t *order,
                                  const float *epad, int64_t br, int64_t bc, int64_t t,
                                  int64_t r, int64_t d, float gamma1, float gamma2, float gamma3, float *sim,
                                  float *stats, void *stream);
 /* Backward of the tensor-core path.  A fused tcgen05 kernel recomputes S, P, A, M per pair on chip (the per-word
- * scalars come from `stats` written by damsm_words_fwd_tc) and emits dS and A as (scaled) fp16 rows
- * [(image, region)][(caption, word)] into `workspace`, one chunk of captions at a time; the K index (caption, word) is
+ * scalars come from `stats` written by damsm_words_fwd_tc) and emits, by TMA store from shared memory, the scaled fp16
+ * dS rows [(image, region)][(caption, word)] and the un-normalised softmax-2 numerators e2 as fp16 rows
+ * [(caption, word)][(image, region padded to a multiple of 64)] into `workspace`, one chunk of captions at a time (one
+ * launch per caption-length group of the chunk: nw <= 32, <= 64, longer); the K index (caption, word) is
  * RAGGED: caption at sorted position s owns columns [koff[s], koff[s+1]) with koff the prefix sums of nw[order[s]]
  * (device AND host copies; the host copy sizes the launches).  chunk_pos_host[0..n_chunks] are the chunk boundaries as
  * positions in the sorted order; a chunk needs fixed_bytes + (koff[s1] - koff[s0]) * col_bytes of workspace.  Per chunk
  * the own tcgen05 GEMM (damsm_gemm_tc) contracts the rows with the packed word rows / vhat, and hmat_tc with each other:
  *   dvhat (bc,R,D) += dS^T qhat   [ACCUMULATED, caller zeroes]     dqpack (koff[br], D) = dS vhat  [OVERWRITTEN, packed rows]
- *   hmat (bc,R,R) += A^T diag(b) A [ACCUMULATED]                   kq (br,T)                       [ACCUMULATED]
+ *   hmat (bc,R,R) += e2^T diag(b/Y^2) e2 = A^T diag(b) A [ACCUMULATED]     kq (br,T)               [ACCUMULATED]
  * qpack16 (koff[br], D) fp16 is scratch for the packed word rows.  damsm_pad_terms_bwd then unpacks dqpack into
  * dqhat (br, q_rows, D) and adds the gradients of the skipped words. */
 DAMSM_API int64_t damsm_words_bwd_tc_col_bytes(int64_t bc, int64_t r);
@@ -260,7 +264,8 @@ DAMSM_API int damsm_project_regions_fwd(const void *x, int dtype, int64_t b, int
                               const float *bias, int64_t n, float *y, float *xhat, void *xhat16,
                               float *norm, float *unorm, void *stream);
 /* dy (b,r,n) fp32 -> dx (b,r+1,k) [CLS rows zero], dw (n,k), db (n): all OVERWRITTEN, each may be NULL.
- * x, w fp32; work: scratch of b*(r+1)*n floats.  Plain GEMMs (cuBLAS, TF32) + a column sum. */
+ * x, w fp32; work: scratch of b*(r+1)*n floats.  Two contractions on the own tcgen05 GEMM (TF32 operands read in
+ * place) + a column sum. */
 DAMSM_API int damsm_project_regions_bwd(const float *x, int64_t b, int64_t r, int64_t k, const float *w, int64_t n,
                               const float *dy, float *work, float *dx, float *dw, float *db, void *stream);
 
