@@ -202,13 +202,13 @@ proj_l2norm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             if (orow[k] < 0) continue;
             const float4 v = *reinterpret_cast<const float4 *>(&tile[(lane >> 3) + 4 * k][cq]);
             const int64_t off = (int64_t)orow[k] * p.N + c + cq;
-            if (p.y) __stcs(reinterpret_cast<float4 *>(p.y + off), v);
+            if (p.y) *reinterpret_cast<float4 *>(p.y + off) = v;
             const float4 h = make_float4(v.x * oinv[k], v.y * oinv[k], v.z * oinv[k], v.w * oinv[k]);
-            if (p.xhat) __stcs(reinterpret_cast<float4 *>(p.xhat + off), h);
+            if (p.xhat) *reinterpret_cast<float4 *>(p.xhat + off) = h;
             if (p.xhat16) {
               const __half2 h01 = __floats2half2_rn(h.x, h.y), h23 = __floats2half2_rn(h.z, h.w);
-              __stcs(reinterpret_cast<uint2 *>(p.xhat16 + off),
-                     make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23)));
+              *reinterpret_cast<uint2 *>(p.xhat16 + off) =
+                  make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
             }
           }
         }
