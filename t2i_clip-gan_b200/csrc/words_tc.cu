@@ -1004,6 +1004,7 @@ int make_map_f16_box(CUtensorMap *m, const void *base, uint64_t n0, uint64_t n1,
 }
 
 static int pick_nt(int T) {
+  if (T < 1) return -1;
   if (T <= 32) return 32;
   if (T <= 64) return 64;
   if (T <= 80) return 80;
